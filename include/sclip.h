@@ -1,0 +1,162 @@
+/*
+ * sclip.h -- C ABI of the B200 (sm_100a) tri-modal contrastive objective.
+ *
+ * Drop-in boundary for the loss tail of Synergy-CLIP's Tri_CLIP.forward:
+ *   reference model.py:247-272  (normalise -> 3 scaled similarity matmuls -> 3 x clip_loss)
+ *   reference model.py:52-58    (contrastive_loss / clip_loss)
+ *   and the autograd backward of those lines (main_pretraining.py:172-173 calls .backward()).
+ * The reference has no native interface of its own (it is pure PyTorch); this header is the
+ * interface a maintainer binds with ctypes.  Everything is plain pointers,
+ * sizes and a cudaStream_t passed as void*: no torch / ATen types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative sclip_status on failure; nothing aborts or throws.
+ *     sclip_last_error() returns a thread-local human-readable description of the last failure.
+ *   - all device buffers are owned by the caller.  The library allocates no device memory; it only
+ *     builds TMA descriptors on the host and passes them as kernel parameters.  `ws` is one caller-allocated blob of sclip_layout.total_bytes
+ *     (256-byte aligned) whose sub-buffers are at the byte offsets sclip_plan() reports.
+ *   - all work is enqueued on the caller's stream; no call synchronises the host.
+ *   - t3 / g3 / loss3 / dt3 are DEVICE pointers to 3 floats ordered (IT, TA, AI)
+ *     (logit_scale_for_IT / _TA / _AI, model.py:80-82).
+ *   - pair / role table (model.py:255,260,265): IT rows=image cols=text, TA rows=text cols=audio,
+ *     AI rows=audio cols=image.  Modalities are ordered (image, text, audio).
+ *   - sharding: a rank owns `rows_local` consecutive rows [row_offset, row_offset+rows_local) of the
+ *     global batch of `rows_global` samples, for all three modalities (what DistributedSampler gives,
+ *     main_pretraining.py:124).  Single GPU: rows_local == rows_global, row_offset == 0.
+ */
+#ifndef SCLIP_H_
+#define SCLIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCLIP_ABI_VERSION 1
+
+typedef enum sclip_status {
+  SCLIP_OK = 0,
+  SCLIP_ERR_ARGUMENT = -1,   /* bad shape / dtype / alignment / null pointer */
+  SCLIP_ERR_CUDA = -2,       /* a CUDA runtime or driver call failed */
+  SCLIP_ERR_UNSUPPORTED = -3 /* device is not sm_100 or the driver lacks cuTensorMapEncodeTiled */
+} sclip_status;
+
+/* dtype of the embeddings handed in and of the embedding gradients handed back */
+typedef enum sclip_dtype { SCLIP_F32 = 0, SCLIP_BF16 = 1 } sclip_dtype;
+
+/* arithmetic mode of the tensor-core contractions
+ *   SCLIP_MATH_F16   : fp16 operands, fp32 accumulate in TMEM (throughput mode; the bf16 I/O contract, 1e-3)
+ *   SCLIP_MATH_F16X3 : every operand split into an fp16 (hi, lo) pair, three tensor-core products per
+ *                      contraction (hi*hi + lo*hi + hi*lo), fp32 accumulate (fp32 parity mode, 1e-5)   */
+typedef enum sclip_math { SCLIP_MATH_F16 = 0, SCLIP_MATH_F16X3 = 1 } sclip_math;
+
+typedef struct sclip_problem {
+  int32_t rows_local;  /* rows of this rank                                   */
+  int32_t rows_global; /* global batch B                                      */
+  int32_t row_offset;  /* first global row owned by this rank                 */
+  int32_t dim;         /* embedding dim D, multiple of 8                      */
+  int32_t dtype;       /* sclip_dtype of img/txt/aud and of dimg/dtxt/daud    */
+  int32_t math;        /* sclip_math                                          */
+  int32_t world;       /* number of ranks sharing the global batch (>= 1)     */
+  int32_t reserved;
+} sclip_problem;
+
+/* Byte offsets into the workspace blob.  Buffers marked [exchange] are the ones the host moves
+ * between ranks (NCCL) when world > 1; everything else is private to the library. */
+typedef struct sclip_layout {
+  uint64_t total_bytes;
+  uint64_t xhat;          /* [3][rows_global][dim] fp16 normalised embeddings; this rank's rows are written by
+                             sclip_prologue at row_offset [exchange: all-gather of the row shards]           */
+  uint64_t xhat_lo;       /* same shape, low halves (SCLIP_MATH_F16X3 only, else == xhat)                    */
+  uint64_t inv_norm;      /* [3][rows_local] fp32                                                            */
+  uint64_t row_part;      /* [3][col_tiles][rows_local] fp32 partial row sums                                */
+  uint64_t col_part;      /* [3][row_tiles][rows_global] fp32 partial column sums                            */
+  uint64_t tile_ref;      /* [3][row_tiles][col_tiles] fp32 exponent reference of each tile                  */
+  uint64_t diag;          /* [3][rows_local] fp32 positive-pair logits L_ii                                  */
+  uint64_t lse_row;       /* [3][rows_local] fp32                                                            */
+  uint64_t lse_col_local; /* [3][rows_global] fp32 column log-sum-exp over this rank's rows [exchange: all-gather] */
+  uint64_t lse_col;       /* [3][rows_global] fp32 column log-sum-exp over all rows                          */
+  uint64_t loss_part;     /* [3] fp32 this rank's share of the three losses [exchange: all-reduce sum]       */
+  uint64_t grad_tiles;    /* [3][rows_local][ld_g] fp16 scaled softmax-gradient strip G'                     */
+  uint64_t grad_tiles_lo; /* low halves (SCLIP_MATH_F16X3 only)                                              */
+  uint64_t dt_part;       /* [3][row_tiles*col_tiles] fp32                                                   */
+  uint64_t dxhat_row;     /* [3][rows_local][dim] fp32 d/dxhat from the row role (+ column role if world==1) */
+  uint64_t dxhat_col;     /* [3][rows_global][dim] fp32 column-role partial sums (world > 1 only)
+                             [exchange: reduce-scatter sum over ranks]                                        */
+  uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed) */
+  int32_t row_tiles;      /* ceil(rows_local / 128)   */
+  int32_t col_tiles;      /* ceil(rows_global / 256)  */
+  int32_t ld_g;           /* leading dimension (elements) of grad_tiles */
+  int32_t reserved;
+} sclip_layout;
+
+int sclip_abi_version(void);
+const char* sclip_last_error(void);
+
+/* Workspace sizing.  Pure host arithmetic; callable without a GPU. */
+int sclip_plan(const sclip_problem* problem, sclip_layout* layout);
+
+/* ---- forward (model.py:248-272) -------------------------------------------------------------- */
+
+/* x / x.norm(p=2, dim=-1, keepdim=True) (model.py:248-250, no epsilon) for this rank's rows of the
+ * three modalities, rounded to the tensor-core operand format and written at row_offset of `xhat`. */
+int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                   void* stream);
+
+/* The three similarity strips (rows_local x rows_global each) with the exp / row-sum / column-sum /
+ * diagonal epilogue (model.py:254-265 and the softmax statistics of model.py:52-58); logits are never
+ * written to memory.  Needs the complete `xhat` (after the all-gather when world > 1). */
+int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3, void* stream);
+
+/* Merge the per-tile statistics into lse_row and lse_col_local. */
+int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream);
+
+/* lse_col = logsumexp over ranks of `col_lse_all` ([world][3][rows_global], NULL => this rank's own
+ * lse_col_local), then this rank's share of the three losses:
+ *   loss_part[p] = ( sum_i (lse_row_i - L_ii) + sum_i (lse_col_{off+i} - L_ii) ) / (2 * rows_global)
+ * written to the workspace and to loss3 (device, 3 floats).  Summed over ranks it is clip_loss. */
+int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_lse_all, float* loss3,
+                       void* stream);
+
+/* ---- backward (autograd of model.py:248-272) --------------------------------------------------- */
+
+/* Recompute the similarity strips and emit the scaled softmax gradient
+ *   G'_p = kappa * c_p * ( (softmax_rows + softmax_cols) / 2 - I ),  c_p = s_p g_p / max_q |s_q g_q|
+ * as fp16 tiles, plus the per-tile partial sums of dL/dlogit_scale.  g3: upstream gradients of the three
+ * losses (device). */
+int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
+
+/* dxhat_row[m] = G'_{rowpair(m)} . xhat_{col modality}   (rows_local x dim, complete)
+ * dxhat_col[m] = G'_{colpair(m)}^T . xhat_{row modality} (rows_global x dim partial sums; world == 1: added
+ *                into dxhat_row by the same accumulator instead). */
+int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
+
+/* Backward of the normalisation: d x = (d - xhat <xhat, d>) / ||x|| with d = dxhat_row (+ col_contrib, the
+ * reduce-scattered column-role gradients [3][rows_local][dim] fp32, NULL when world == 1), times grad_mult
+ * (1, or world when the caller's DDP wrapper will average over ranks).  Also finishes dlogit_scale:
+ * dt3[p] = grad_mult * (this rank's share), device, 3 floats.
+ * dimg/dtxt/daud have the dtype of the problem unless out_f32 != 0. */
+int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                          const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,
+                          void* dtxt, void* daud, int out_f32, float* dt3, void* stream);
+
+/* ---- single-GPU convenience (world == 1): the whole tail in two calls --------------------------- */
+int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                  const float* t3, float* loss3, void* stream);
+int sclip_backward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                   const float* t3, const float* g3, void* dimg, void* dtxt, void* daud, int out_f32, float* dt3,
+                   void* stream);
+
+/* ---- building block exposed for tests and for the zero-shot scorers (model.py:126-203) ---------- */
+/* C[M x N] (fp32, ld ldc) = alpha * A . B with fp16 operands.
+ * a_mn == 0: A is stored [M][K] (K contiguous);  a_mn != 0: A is stored [K][M] (M contiguous).
+ * b_mn == 0: B is stored [N][K] (K contiguous);  b_mn != 0: B is stored [K][N] (N contiguous).  */
+int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c, int64_t ldc,
+                   int m, int n, int k, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCLIP_H_ */

@@ -1,0 +1,151 @@
+// Shared host/device definitions of the sclip library (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/sclip.h"
+
+namespace sclip {
+
+// ------------------------------------------------------------------ tile geometry of the tensor-core kernels
+constexpr int BM = 128;      // rows of the accumulator tile (TMEM lanes)
+constexpr int BN = 256;      // columns of the accumulator tile (TMEM columns, fp32)
+constexpr int BK = 64;       // fp16 elements per k block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;   // k extent of one tcgen05.mma kind::f16
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int MN_BOX_BYTES = 64 * BK * 2;    // one 64(mn) x 64(k) box of an MN-major operand
+constexpr int kStages = 2;                   // per CTA; two CTAs are co-resident per SM
+constexpr int kTileThreads = 192;            // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
+constexpr int kTileSmemBytes = kStages * STAGE_BYTES + 1024;  // + slack for the 1024-byte alignment
+
+constexpr float kKappa = 32768.0f;           // scale of the fp16 softmax-gradient tiles (|G'| <= kappa)
+constexpr float kFastPathMaxScale = 40.0f;   // exp(-2 s) must stay a normal fp32 number for the fixed reference
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kOperandScaleX3 = 256.0f;    // xhat is stored as 256*xhat in the F16X3 mode (keeps lo parts normal)
+
+constexpr int kMaxSegments = 6;
+constexpr int kMaxJobs = 6;
+constexpr int kFwdMaps = 12;    // tensor maps carried in the kernel parameters (128 B each)
+constexpr int kBwdMaps = 18;
+constexpr int kGemmMaps = 24;
+
+// One k range of a tile contraction: acc += A_seg(m0.., :) . B_seg(n0.., :)^T
+struct Segment {
+  int map_a;   // index into the tensor-map table of the kernel parameters
+  int map_b;
+  int a_mn;    // 0: operand stored [rows][k] (K-major)   1: stored [k][rows] (MN-major)
+  int b_mn;
+  int num_kb;  // number of BK-wide k blocks
+};
+
+struct Job {
+  Segment seg[kMaxSegments];
+  int nseg;
+  int m_tiles;   // BM tiles
+  int n_tiles;   // BN tiles
+  int tile_base; // first linear tile id of this job inside a batched launch
+};
+
+// thread-local error text (defined in sclip_api.cu)
+void set_error(const char* fmt, ...);
+
+#define SCLIP_CUDA_OK(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::sclip::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SCLIP_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+// pair p: rows = modality p, cols = modality (p + 1) % 3  (model.py:255,260,265)
+__host__ __device__ inline int pair_row_modality(int p) { return p; }
+__host__ __device__ inline int pair_col_modality(int p) { return (p + 1) % 3; }
+// modality m takes the row role in pair m and the column role in pair (m + 2) % 3
+__host__ __device__ inline int modality_row_pair(int m) { return m; }
+__host__ __device__ inline int modality_col_pair(int m) { return (m + 2) % 3; }
+
+// ------------------------------------------------------------------ kernel launchers (defined in the .cu files)
+struct Workspace {  // resolved device pointers of one workspace blob
+  sclip_problem pb;
+  sclip_layout lay;
+  uint8_t* base;
+  __half* xhat[3];
+  __half* xhat_lo[3];
+  float* inv_norm;
+  float* row_part;
+  float* col_part;
+  float* tile_ref;
+  float* diag;
+  float* lse_row;
+  float* lse_col_local;
+  float* lse_col;
+  float* loss_part;
+  __half* g[3];
+  __half* g_lo[3];
+  float* dt_part;
+  float* dxhat_row;
+  float* dxhat_col;
+  int* status;
+};
+
+struct FwdParams {
+  CUtensorMap maps[kFwdMaps];
+  Job jobs[3];
+  const float* t3;
+  float* row_part;
+  float* col_part;
+  float* tile_ref;
+  float* diag;
+  int rows_local, rows_global, row_offset;
+  int nti, ntj;
+  float acc_scale;  // accumulator -> cosine (1 in F16 mode, 2^-16 in F16X3 mode)
+};
+
+struct BwdParams {
+  CUtensorMap maps[kBwdMaps];
+  Job jobs[3];
+  int store_map[3];      // tensor map (box 64 x 128) for the G' tile stores, per pair
+  int store_map_lo[3];   // low halves (F16X3) or -1
+  const float* t3;
+  const float* g3;
+  const float* lse_row;
+  const float* lse_col;
+  float* dt_part;
+  int rows_local, rows_global, row_offset;
+  int nti, ntj;
+  float acc_scale;
+};
+
+struct GemmParams {
+  CUtensorMap maps[kGemmMaps];
+  Job jobs[kMaxJobs];
+  float* out[kMaxJobs];
+  long long ldc[kMaxJobs];
+  int m[kMaxJobs];
+  int n[kMaxJobs];
+  int njobs;
+  int total_tiles;
+  const float* t3;   // when non-null alpha = alpha0 * max_q |exp(t_q) g_q| (backward); else alpha = alpha0
+  const float* g3;
+  float alpha0;
+};
+
+int launch_forward_tiles(const FwdParams& p, cudaStream_t stream);
+int launch_backward_tiles(const BwdParams& p, cudaStream_t stream);
+int launch_gemm(const GemmParams& p, cudaStream_t stream);
+
+int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream);
+int launch_forward_reduce(const Workspace& w, cudaStream_t stream);
+int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream);
+int launch_backward_finish(const Workspace& w, const void* const x3[3], const float* t3, const float* g3,
+                           const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, float* dt3,
+                           cudaStream_t stream);
+
+}  // namespace sclip

@@ -1,0 +1,508 @@
+// C ABI of the sclip library (include/sclip.h): argument checking, workspace layout, TMA descriptor
+// construction and the stage launchers.  Host code only; the kernels live in sclip_tc.cu / sclip_simt.cu.
+#include <cstdarg>
+#include <cstring>
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+
+namespace sclip {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+int check_problem(const sclip_problem* pb) {
+  if (pb == nullptr) {
+    set_error("problem is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (pb->rows_local < 1 || pb->rows_global < pb->rows_local || pb->row_offset < 0 ||
+      pb->row_offset + pb->rows_local > pb->rows_global) {
+    set_error("bad row partition: rows_local=%d rows_global=%d row_offset=%d", pb->rows_local, pb->rows_global,
+              pb->row_offset);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (pb->dim < 8 || pb->dim % 8 != 0) {
+    set_error("dim=%d must be a positive multiple of 8 (16-byte rows for TMA)", pb->dim);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (pb->dtype != SCLIP_F32 && pb->dtype != SCLIP_BF16) {
+    set_error("dtype=%d is neither SCLIP_F32 nor SCLIP_BF16", pb->dtype);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (pb->math != SCLIP_MATH_F16 && pb->math != SCLIP_MATH_F16X3) {
+    set_error("math=%d is neither SCLIP_MATH_F16 nor SCLIP_MATH_F16X3", pb->math);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (pb->world < 1 || (pb->world == 1 && pb->rows_local != pb->rows_global)) {
+    set_error("world=%d inconsistent with rows_local=%d rows_global=%d", pb->world, pb->rows_local, pb->rows_global);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return SCLIP_OK;
+}
+
+int plan(const sclip_problem* pb, sclip_layout* lay) {
+  int rc = check_problem(pb);
+  if (rc) return rc;
+  if (lay == nullptr) {
+    set_error("layout is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  memset(lay, 0, sizeof(*lay));
+  const uint64_t bl = pb->rows_local, bg = pb->rows_global, d = pb->dim;
+  const bool x3 = pb->math == SCLIP_MATH_F16X3;
+  lay->row_tiles = ceil_div(pb->rows_local, BM);
+  lay->col_tiles = ceil_div(pb->rows_global, BN);
+  lay->ld_g = static_cast<int32_t>(align_up(bg, 64));
+  const uint64_t nti = lay->row_tiles, ntj = lay->col_tiles, ldg = lay->ld_g;
+  uint64_t off = 0;
+  auto take = [&](uint64_t bytes) {
+    const uint64_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  lay->xhat = take(3 * bg * d * 2);
+  lay->xhat_lo = x3 ? take(3 * bg * d * 2) : lay->xhat;
+  lay->inv_norm = take(3 * bl * 4);
+  lay->row_part = take(3 * ntj * bl * 4);
+  lay->col_part = take(3 * nti * bg * 4);
+  lay->tile_ref = take(3 * nti * ntj * 4);
+  lay->diag = take(3 * bl * 4);
+  lay->lse_row = take(3 * bl * 4);
+  lay->lse_col_local = take(3 * bg * 4);
+  lay->lse_col = take(3 * bg * 4);
+  lay->loss_part = take(3 * 4);
+  lay->grad_tiles = take(3 * bl * ldg * 2);
+  lay->grad_tiles_lo = x3 ? take(3 * bl * ldg * 2) : lay->grad_tiles;
+  lay->dt_part = take(3 * nti * ntj * 4);
+  lay->dxhat_row = take(3 * bl * d * 4);
+  lay->dxhat_col = pb->world > 1 ? take(3 * bg * d * 4) : lay->dxhat_row;
+  lay->status = take(4 * 4);
+  lay->total_bytes = off;
+  return SCLIP_OK;
+}
+
+int resolve(const sclip_problem* pb, void* ws, Workspace* w) {
+  int rc = plan(pb, &w->lay);
+  if (rc) return rc;
+  if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255u) != 0) {
+    set_error("workspace pointer must be non-null and 256-byte aligned");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  w->pb = *pb;
+  uint8_t* b = static_cast<uint8_t*>(ws);
+  const sclip_layout& l = w->lay;
+  const size_t bl = pb->rows_local, bg = pb->rows_global, d = pb->dim, ldg = l.ld_g;
+  w->base = b;
+  for (int m = 0; m < 3; ++m) {
+    w->xhat[m] = reinterpret_cast<__half*>(b + l.xhat) + m * bg * d;
+    w->xhat_lo[m] = reinterpret_cast<__half*>(b + l.xhat_lo) + m * bg * d;
+    w->g[m] = reinterpret_cast<__half*>(b + l.grad_tiles) + m * bl * ldg;
+    w->g_lo[m] = reinterpret_cast<__half*>(b + l.grad_tiles_lo) + m * bl * ldg;
+  }
+  w->inv_norm = reinterpret_cast<float*>(b + l.inv_norm);
+  w->row_part = reinterpret_cast<float*>(b + l.row_part);
+  w->col_part = reinterpret_cast<float*>(b + l.col_part);
+  w->tile_ref = reinterpret_cast<float*>(b + l.tile_ref);
+  w->diag = reinterpret_cast<float*>(b + l.diag);
+  w->lse_row = reinterpret_cast<float*>(b + l.lse_row);
+  w->lse_col_local = reinterpret_cast<float*>(b + l.lse_col_local);
+  w->lse_col = reinterpret_cast<float*>(b + l.lse_col);
+  w->loss_part = reinterpret_cast<float*>(b + l.loss_part);
+  w->dt_part = reinterpret_cast<float*>(b + l.dt_part);
+  w->dxhat_row = reinterpret_cast<float*>(b + l.dxhat_row);
+  w->dxhat_col = reinterpret_cast<float*>(b + l.dxhat_col);
+  w->status = reinterpret_cast<int*>(b + l.status);
+  return SCLIP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ TMA descriptors
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// fp16 matrix [outer][inner] (inner contiguous, row pitch ld elements); box = box_inner x box_outer, 128-byte swizzle
+int make_map(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+             uint32_t box_outer) {
+  auto fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SCLIP_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (ld * 2) % 16 != 0) {
+    set_error("TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ptr=%p ld=%llu)", ptr,
+              static_cast<unsigned long long>(ld));
+    return SCLIP_ERR_ARGUMENT;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu ld=%llu box=%ux%u)", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return SCLIP_ERR_CUDA;
+  }
+  return SCLIP_OK;
+}
+
+// tensor-map slots of a workspace
+enum MapSlot {
+  kXhatRowsK = 0,     // + m : xhat[m] local rows, K-major A box 64 x 128
+  kXhatColsK = 3,     // + m : xhat[m] all rows,   K-major B box 64 x 256
+  kXloRowsK = 6,
+  kXloColsK = 9,
+  kGK = 12,           // + p : G'[p] [rows_local][rows_global], box 64 x 128 (store target and K-major A operand)
+  kGloK = 15,
+  kGMN = 18,          // + p : same memory, box 64 x 64 (MN-major A operand = G'^T)
+  kGloMN = 21,
+  kXhatAllMN = 24,    // + m : xhat[m] all rows, box 64(d) x 64(rows): MN-major B operand, k = global row
+  kXhatLocMN = 27,    // + m : xhat[m] local rows, MN-major B operand, k = local row
+  kXloAllMN = 30,
+  kXloLocMN = 33,
+  kNumSlots = 36
+};
+
+// Encode the descriptor of one slot.
+int encode_slot(const Workspace& w, int slot, CUtensorMap* out) {
+  const sclip_problem& pb = w.pb;
+  const uint64_t bl = pb.rows_local, bg = pb.rows_global, d = pb.dim, ldg = w.lay.ld_g;
+  const int m = slot % 3;
+  const __half* loc = w.xhat[m] + static_cast<size_t>(pb.row_offset) * d;
+  const __half* loc_lo = w.xhat_lo[m] + static_cast<size_t>(pb.row_offset) * d;
+  switch (slot - m) {
+    case kXhatRowsK: return make_map(out, loc, d, bl, d, BK, BM);
+    case kXhatColsK: return make_map(out, w.xhat[m], d, bg, d, BK, BN);
+    case kXloRowsK: return make_map(out, loc_lo, d, bl, d, BK, BM);
+    case kXloColsK: return make_map(out, w.xhat_lo[m], d, bg, d, BK, BN);
+    case kGK: return make_map(out, w.g[m], bg, bl, ldg, 64, BM);
+    case kGloK: return make_map(out, w.g_lo[m], bg, bl, ldg, 64, BM);
+    case kGMN: return make_map(out, w.g[m], bg, bl, ldg, 64, BK);
+    case kGloMN: return make_map(out, w.g_lo[m], bg, bl, ldg, 64, BK);
+    case kXhatAllMN: return make_map(out, w.xhat[m], d, bg, d, 64, BK);
+    case kXhatLocMN: return make_map(out, loc, d, bl, d, 64, BK);
+    case kXloAllMN: return make_map(out, w.xhat_lo[m], d, bg, d, 64, BK);
+    case kXloLocMN: return make_map(out, loc_lo, d, bl, d, 64, BK);
+  }
+  set_error("internal: unknown tensor-map slot %d", slot);
+  return SCLIP_ERR_ARGUMENT;
+}
+
+// Collects the descriptors one kernel launch needs into the table carried by its parameters.
+struct MapTable {
+  const Workspace& w;
+  CUtensorMap* dst;
+  int cap;
+  int count = 0;
+  int rc = 0;
+  int local[kNumSlots];
+  MapTable(const Workspace& ws, CUtensorMap* d, int c) : w(ws), dst(d), cap(c) {
+    for (int i = 0; i < kNumSlots; ++i) local[i] = -1;
+  }
+  int use(int slot) {
+    if (local[slot] >= 0) return local[slot];
+    if (count >= cap) {
+      set_error("internal: tensor-map table overflow");
+      rc = SCLIP_ERR_ARGUMENT;
+      return 0;
+    }
+    const int r = encode_slot(w, slot, &dst[count]);
+    if (r) rc = r;
+    local[slot] = count;
+    return count++;
+  }
+};
+
+Segment seg(int a, int b, int a_mn, int b_mn, int num_kb) { return Segment{a, b, a_mn, b_mn, num_kb}; }
+
+// similarity job of pair p (forward and the backward recompute)
+void similarity_job(const Workspace& w, MapTable& t, int p, Job* job) {
+  const int rm = pair_row_modality(p), cm = pair_col_modality(p);
+  const int nkb = ceil_div(w.pb.dim, BK);
+  memset(job, 0, sizeof(*job));
+  job->seg[0] = seg(t.use(kXhatRowsK + rm), t.use(kXhatColsK + cm), 0, 0, nkb);
+  job->nseg = 1;
+  if (w.pb.math == SCLIP_MATH_F16X3) {
+    job->seg[1] = seg(t.use(kXloRowsK + rm), t.use(kXhatColsK + cm), 0, 0, nkb);
+    job->seg[2] = seg(t.use(kXhatRowsK + rm), t.use(kXloColsK + cm), 0, 0, nkb);
+    job->nseg = 3;
+  }
+  job->m_tiles = w.lay.row_tiles;
+  job->n_tiles = w.lay.col_tiles;
+}
+
+}  // namespace
+}  // namespace sclip
+
+using namespace sclip;
+
+extern "C" {
+
+int sclip_abi_version(void) { return SCLIP_ABI_VERSION; }
+const char* sclip_last_error(void) { return g_error; }
+
+int sclip_plan(const sclip_problem* problem, sclip_layout* layout) { return plan(problem, layout); }
+
+int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                   void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  const void* x3[3] = {img, txt, aud};
+  for (int m = 0; m < 3; ++m)
+    if (x3[m] == nullptr || (reinterpret_cast<uintptr_t>(x3[m]) & 15u) != 0) {
+      set_error("embedding pointer %d must be non-null and 16-byte aligned", m);
+      return SCLIP_ERR_ARGUMENT;
+    }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SCLIP_CUDA_OK(cudaMemsetAsync(w.status, 0, 16, st));
+  return launch_prologue(w, x3, st);
+}
+
+int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr) {
+    set_error("t3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  MapTable tab(w, p.maps, kFwdMaps);
+  for (int q = 0; q < 3; ++q) similarity_job(w, tab, q, &p.jobs[q]);
+  if (tab.rc) return tab.rc;
+  p.t3 = t3;
+  p.row_part = w.row_part;
+  p.col_part = w.col_part;
+  p.tile_ref = w.tile_ref;
+  p.diag = w.diag;
+  p.rows_local = w.pb.rows_local;
+  p.rows_global = w.pb.rows_global;
+  p.row_offset = w.pb.row_offset;
+  p.nti = w.lay.row_tiles;
+  p.ntj = w.lay.col_tiles;
+  p.acc_scale = w.pb.math == SCLIP_MATH_F16X3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
+  return launch_forward_tiles(p, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  return launch_forward_reduce(w, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_lse_all, float* loss3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  return launch_forward_loss(w, col_lse_all, loss3, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr || g3 == nullptr) {
+    set_error("t3 / g3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  BwdParams p;
+  memset(&p, 0, sizeof(p));
+  MapTable tab(w, p.maps, kBwdMaps);
+  const bool x3 = w.pb.math == SCLIP_MATH_F16X3;
+  for (int q = 0; q < 3; ++q) {
+    similarity_job(w, tab, q, &p.jobs[q]);
+    p.store_map[q] = tab.use(kGK + q);
+    p.store_map_lo[q] = x3 ? tab.use(kGloK + q) : -1;
+  }
+  if (tab.rc) return tab.rc;
+  p.t3 = t3;
+  p.g3 = g3;
+  p.lse_row = w.lse_row;
+  p.lse_col = w.lse_col;
+  p.dt_part = w.dt_part;
+  p.rows_local = w.pb.rows_local;
+  p.rows_global = w.pb.rows_global;
+  p.row_offset = w.pb.row_offset;
+  p.nti = w.lay.row_tiles;
+  p.ntj = w.lay.col_tiles;
+  p.acc_scale = x3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
+  return launch_backward_tiles(p, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr || g3 == nullptr) {
+    set_error("t3 / g3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const sclip_problem& pb = w.pb;
+  const bool x3 = pb.math == SCLIP_MATH_F16X3;
+  const int kb_g = ceil_div(pb.rows_global, BK), kb_l = ceil_div(pb.rows_local, BK);
+  const size_t bl = pb.rows_local, bg = pb.rows_global, d = pb.dim;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  MapTable tab(w, p.maps, kGemmMaps);
+  p.t3 = t3;
+  p.g3 = g3;
+  // dXhat = (max_q |s_q g_q| / (kappa B)) G' Xhat ; operands of the F16X3 mode carry an extra factor 256
+  p.alpha0 = 1.0f / (kKappa * static_cast<float>(pb.rows_global)) / (x3 ? kOperandScaleX3 : 1.0f);
+  int nj = 0, tiles = 0;
+  auto add_role = [&](Job& job, int m, bool row_role) {
+    if (row_role) {  // G'_{pair m} (rows_local x rows_global, K-major) . xhat_{col modality} (k = global row)
+      const int pr = modality_row_pair(m), cm = pair_col_modality(pr);
+      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
+      if (x3) {
+        job.seg[job.nseg++] = seg(tab.use(kGloK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
+        job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
+      }
+    } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
+      const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
+      job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
+      if (x3) {
+        job.seg[job.nseg++] = seg(tab.use(kGloMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
+        job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXloLocMN + rm), 1, 1, kb_l);
+      }
+    }
+  };
+  for (int m = 0; m < 3; ++m) {
+    Job& job = p.jobs[nj];
+    add_role(job, m, true);
+    if (pb.world == 1) add_role(job, m, false);
+    job.m_tiles = ceil_div(pb.rows_local, BM);
+    job.n_tiles = ceil_div(pb.dim, BN);
+    job.tile_base = tiles;
+    tiles += job.m_tiles * job.n_tiles;
+    p.out[nj] = w.dxhat_row + m * bl * d;
+    p.ldc[nj] = pb.dim;
+    p.m[nj] = pb.rows_local;
+    p.n[nj] = pb.dim;
+    ++nj;
+  }
+  if (pb.world > 1) {
+    for (int m = 0; m < 3; ++m) {
+      Job& job = p.jobs[nj];
+      add_role(job, m, false);
+      job.m_tiles = ceil_div(pb.rows_global, BM);
+      job.n_tiles = ceil_div(pb.dim, BN);
+      job.tile_base = tiles;
+      tiles += job.m_tiles * job.n_tiles;
+      p.out[nj] = w.dxhat_col + m * bg * d;
+      p.ldc[nj] = pb.dim;
+      p.m[nj] = pb.rows_global;
+      p.n[nj] = pb.dim;
+      ++nj;
+    }
+  }
+  if (tab.rc) return tab.rc;
+  p.njobs = nj;
+  p.total_tiles = tiles;
+  return launch_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                          const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,
+                          void* dtxt, void* daud, int out_f32, float* dt3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  const void* x3[3] = {img, txt, aud};
+  void* dx3[3] = {dimg, dtxt, daud};
+  for (int m = 0; m < 3; ++m)
+    if (x3[m] == nullptr || dx3[m] == nullptr || (reinterpret_cast<uintptr_t>(dx3[m]) & 15u) != 0) {
+      set_error("embedding / gradient pointer %d must be non-null and 16-byte aligned", m);
+      return SCLIP_ERR_ARGUMENT;
+    }
+  if (w.pb.world > 1 && col_contrib == nullptr) {
+    set_error("world > 1 needs the reduce-scattered column-role gradients (col_contrib)");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_backward_finish(w, x3, t3, g3, col_contrib, grad_mult, dx3, out_f32, dt3,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                  const float* t3, float* loss3, void* stream) {
+  if (problem != nullptr && problem->world != 1) {
+    set_error("sclip_forward is the single-GPU entry point (world must be 1); use the stage calls when sharded");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  int rc = sclip_prologue(problem, ws, img, txt, aud, stream);
+  if (!rc) rc = sclip_forward_tiles(problem, ws, t3, stream);
+  if (!rc) rc = sclip_forward_reduce(problem, ws, stream);
+  if (!rc) rc = sclip_forward_loss(problem, ws, nullptr, loss3, stream);
+  return rc;
+}
+
+int sclip_backward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
+                   const float* t3, const float* g3, void* dimg, void* dtxt, void* daud, int out_f32, float* dt3,
+                   void* stream) {
+  if (problem != nullptr && problem->world != 1) {
+    set_error("sclip_backward is the single-GPU entry point (world must be 1); use the stage calls when sharded");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  int rc = sclip_backward_tiles(problem, ws, t3, g3, stream);
+  if (!rc) rc = sclip_backward_gemms(problem, ws, t3, g3, stream);
+  if (!rc)
+    rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32, dt3,
+                               stream);
+  return rc;
+}
+
+int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t ldb, int b_mn, float* c, int64_t ldc,
+                   int m, int n, int k, float alpha, void* stream) {
+  if (a == nullptr || b == nullptr || c == nullptr || m < 1 || n < 1 || k < 1 || n % 4 != 0 || ldc % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(c) & 15u) != 0) {
+    set_error("sclip_gemm_f16: bad argument (null pointer, non-positive size, n or ldc not a multiple of 4, or alignment)");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = a_mn ? make_map(&p.maps[0], a, m, k, lda, 64, BK) : make_map(&p.maps[0], a, k, m, lda, BK, BM);
+  if (!rc) rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK)};
+  p.jobs[0].nseg = 1;
+  p.jobs[0].m_tiles = ceil_div(m, BM);
+  p.jobs[0].n_tiles = ceil_div(n, BN);
+  p.jobs[0].tile_base = 0;
+  p.out[0] = c;
+  p.ldc[0] = ldc;
+  p.m[0] = m;
+  p.n[0] = n;
+  p.njobs = 1;
+  p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles;
+  p.alpha0 = alpha;
+  return launch_gemm(p, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,365 @@
+// HBM-bound SIMT kernels around the tensor-core tiles: the fused normalise + cast prologue
+// (model.py:248-250), the merge of per-tile softmax statistics into log-sum-exps and the three
+// losses (model.py:52-58), and the backward of the normalisation plus dL/dlogit_scale.
+#include "common.cuh"
+
+namespace sclip {
+namespace {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) v += __shfl_xor_sync(0xffffffffu, v, w);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) v += __shfl_xor_sync(0xffffffffu, v, w);
+  return v;
+}
+
+// 8 consecutive elements of a row as fp32 (16-byte / 32-byte coalesced vector loads)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 raw;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = raw;
+}
+__device__ __forceinline__ uint4 pack8_half(const float (&v)[8]) {
+  uint4 raw;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return raw;
+}
+
+constexpr int kRowsPerBlock = 8;  // one warp per embedding row
+
+// ------------------------------------------------------------------------------------------------ prologue
+// x / ||x||_2 (no epsilon: a zero row gives NaN exactly like model.py:248), rounded to fp16 operands.
+// F16X3: operand = 256 * xhat split into hi + lo fp16 halves.
+struct PrologueArgs {
+  const void* x[3];
+  __half* hi[3];
+  __half* lo[3];
+  float* inv_norm;
+  int rows, dim;
+  int row_offset;
+  float opscale;
+  int split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kRowsPerBlock * 32) prologue_kernel(const PrologueArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kRowsPerBlock + warp;
+  const int m = blockIdx.y;
+  if (row >= a.rows) return;
+  const T* xr = static_cast<const T*>(a.x[m]) + static_cast<size_t>(row) * a.dim;
+  float ss = 0.f;
+  for (int i = lane * 8; i < a.dim; i += 256) {
+    float v[8];
+    load8(xr + i, v);
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part = fmaf(v[k], v[k], part);
+    ss += part;
+  }
+  ss = warp_sum_f(ss);
+  const float nrm = sqrtf(ss);
+  if (lane == 0) a.inv_norm[static_cast<size_t>(m) * a.rows + row] = 1.0f / nrm;
+  __half* hr = a.hi[m] + static_cast<size_t>(a.row_offset + row) * a.dim;
+  __half* lr = a.lo[m] + static_cast<size_t>(a.row_offset + row) * a.dim;
+  for (int i = lane * 8; i < a.dim; i += 256) {
+    float v[8];
+    load8(xr + i, v);  // second read hits L1/L2
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (v[k] / nrm) * a.opscale;
+    *reinterpret_cast<uint4*>(hr + i) = pack8_half(v);
+    if (a.split) {
+      float r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = v[k] - __half2float(__float2half_rn(v[k]));
+      *reinterpret_cast<uint4*>(lr + i) = pack8_half(r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward reduce
+struct ReduceArgs {
+  const float* row_part;
+  const float* col_part;
+  const float* tile_ref;
+  float* lse_row;
+  float* lse_col_local;
+  int* status;
+  int rows_local, rows_global, nti, ntj;
+};
+
+__global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int p = blockIdx.y;
+  bool bad = false;
+  if (i < a.rows_local) {
+    const int ti = i / BM;
+    const float* ref = a.tile_ref + (static_cast<size_t>(p) * a.nti + ti) * a.ntj;
+    float R = -INFINITY;
+    for (int tj = 0; tj < a.ntj; ++tj) R = fmaxf(R, ref[tj]);
+    float sum = 0.f;
+    for (int tj = 0; tj < a.ntj; ++tj)
+      sum += a.row_part[(static_cast<size_t>(p) * a.ntj + tj) * a.rows_local + i] * __expf(ref[tj] - R);
+    const float lse = R + logf(sum);
+    a.lse_row[static_cast<size_t>(p) * a.rows_local + i] = lse;
+    bad |= !isfinite(lse);
+  }
+  if (i < a.rows_global) {
+    const int tj = i / BN;
+    float R = -INFINITY;
+    for (int ti = 0; ti < a.nti; ++ti) R = fmaxf(R, a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj]);
+    float sum = 0.f;
+    for (int ti = 0; ti < a.nti; ++ti)
+      sum += a.col_part[(static_cast<size_t>(p) * a.nti + ti) * a.rows_global + i] *
+             __expf(a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj] - R);
+    const float lse = R + logf(sum);
+    a.lse_col_local[static_cast<size_t>(p) * a.rows_global + i] = lse;
+    bad |= !isfinite(lse);
+  }
+  if (bad) atomicOr(a.status, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ forward loss
+struct LossArgs {
+  const float* lse_row;
+  const float* lse_col_local;
+  const float* col_lse_all;  // [world][3][rows_global] or null
+  const float* diag;
+  float* lse_col;
+  float* loss_part;
+  float* loss3;
+  int rows_local, rows_global, row_offset, world;
+};
+
+__global__ void __launch_bounds__(1024) forward_loss_kernel(const LossArgs a) {
+  __shared__ double red[32];
+  const int p = blockIdx.x;
+  float* lse_col = a.lse_col + static_cast<size_t>(p) * a.rows_global;
+  for (int j = threadIdx.x; j < a.rows_global; j += blockDim.x) {
+    float v;
+    if (a.col_lse_all == nullptr) {
+      v = a.lse_col_local[static_cast<size_t>(p) * a.rows_global + j];
+    } else {
+      float mx = -INFINITY;
+      for (int w = 0; w < a.world; ++w)
+        mx = fmaxf(mx, a.col_lse_all[(static_cast<size_t>(w) * 3 + p) * a.rows_global + j]);
+      float sum = 0.f;
+      for (int w = 0; w < a.world; ++w)
+        sum += expf(a.col_lse_all[(static_cast<size_t>(w) * 3 + p) * a.rows_global + j] - mx);
+      v = mx + logf(sum);
+    }
+    lse_col[j] = v;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < a.rows_local; i += blockDim.x) {
+    const double d = a.diag[static_cast<size_t>(p) * a.rows_local + i];
+    acc += (static_cast<double>(a.lse_row[static_cast<size_t>(p) * a.rows_local + i]) - d) +
+           (static_cast<double>(lse_col[a.row_offset + i]) - d);
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) {
+      const float loss = static_cast<float>(v / (2.0 * a.rows_global));
+      a.loss_part[p] = loss;
+      if (a.loss3 != nullptr) a.loss3[p] = loss;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward finish
+struct FinishArgs {
+  const void* x[3];
+  void* dx[3];
+  const float* dxhat_row;    // [3][rows][dim]
+  const float* col_contrib;  // [3][rows][dim] or null
+  const float* inv_norm;
+  int rows, dim;
+  float grad_mult;
+};
+
+// d x = (d - xhat <xhat, d>) / ||x||, with xhat recomputed in fp32 from the caller's embeddings
+template <typename T, typename TO>
+__global__ void __launch_bounds__(kRowsPerBlock * 32) backward_finish_kernel(const FinishArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kRowsPerBlock + warp;
+  const int m = blockIdx.y;
+  if (row >= a.rows) return;
+  const size_t base = (static_cast<size_t>(m) * a.rows + row) * a.dim;
+  const T* xr = static_cast<const T*>(a.x[m]) + static_cast<size_t>(row) * a.dim;
+  TO* outr = static_cast<TO*>(a.dx[m]) + static_cast<size_t>(row) * a.dim;
+  const float inv = a.inv_norm[static_cast<size_t>(m) * a.rows + row];
+  float dot = 0.f;
+  for (int i = lane * 8; i < a.dim; i += 256) {
+    float x[8], d[8];
+    load8(xr + i, x);
+    load8(a.dxhat_row + base + i, d);
+    if (a.col_contrib != nullptr) {
+      float e[8];
+      load8(a.col_contrib + base + i, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += e[k];
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part = fmaf(x[k] * inv, d[k], part);
+    dot += part;
+  }
+  dot = warp_sum_f(dot);
+  const float scale = inv * a.grad_mult;
+  for (int i = lane * 8; i < a.dim; i += 256) {
+    float x[8], d[8], o[8];
+    load8(xr + i, x);
+    load8(a.dxhat_row + base + i, d);
+    if (a.col_contrib != nullptr) {
+      float e[8];
+      load8(a.col_contrib + base + i, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += e[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = (d[k] - (x[k] * inv) * dot) * scale;
+    store8(outr + i, o);
+  }
+}
+
+struct DtArgs {
+  const float* dt_part;
+  const float* t3;
+  const float* g3;
+  float* dt3;
+  int ntiles;
+  int rows_global;
+  float grad_mult;
+};
+
+__global__ void __launch_bounds__(1024) dt_finish_kernel(const DtArgs a) {
+  __shared__ double red[32];
+  const int p = blockIdx.x;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < a.ntiles; i += blockDim.x) acc += a.dt_part[static_cast<size_t>(p) * a.ntiles + i];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) {
+      float mx = 0.f;
+      for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(a.t3[r]) * a.g3[r]));
+      a.dt3[p] = static_cast<float>(v * (static_cast<double>(mx) / (static_cast<double>(kKappa) * a.rows_global)) * a.grad_mult);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream) {
+  PrologueArgs a;
+  for (int m = 0; m < 3; ++m) {
+    a.x[m] = x3[m];
+    a.hi[m] = w.xhat[m];
+    a.lo[m] = w.xhat_lo[m];
+  }
+  a.inv_norm = w.inv_norm;
+  a.rows = w.pb.rows_local;
+  a.dim = w.pb.dim;
+  a.row_offset = w.pb.row_offset;
+  a.split = w.pb.math == SCLIP_MATH_F16X3;
+  a.opscale = a.split ? kOperandScaleX3 : 1.0f;
+  dim3 grid((a.rows + kRowsPerBlock - 1) / kRowsPerBlock, 3);
+  if (w.pb.dtype == SCLIP_F32)
+    prologue_kernel<float><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
+  else
+    prologue_kernel<__nv_bfloat16><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_forward_reduce(const Workspace& w, cudaStream_t stream) {
+  ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.lse_row, w.lse_col_local, w.status,
+               w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, w.lay.col_tiles};
+  const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
+  dim3 grid((n + 255) / 256, 3);
+  forward_reduce_kernel<<<grid, 256, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream) {
+  LossArgs a{w.lse_row, w.lse_col_local, col_lse_all, w.diag, w.lse_col, w.loss_part, loss3,
+             w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, w.pb.world};
+  forward_loss_kernel<<<3, 1024, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_backward_finish(const Workspace& w, const void* const x3[3], const float* t3, const float* g3,
+                           const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, float* dt3,
+                           cudaStream_t stream) {
+  FinishArgs a;
+  for (int m = 0; m < 3; ++m) {
+    a.x[m] = x3[m];
+    a.dx[m] = dx3[m];
+  }
+  a.dxhat_row = w.dxhat_row;
+  a.col_contrib = col_contrib;
+  a.inv_norm = w.inv_norm;
+  a.rows = w.pb.rows_local;
+  a.dim = w.pb.dim;
+  a.grad_mult = grad_mult;
+  dim3 grid((a.rows + kRowsPerBlock - 1) / kRowsPerBlock, 3);
+  const int threads = kRowsPerBlock * 32;
+  if (w.pb.dtype == SCLIP_F32)
+    backward_finish_kernel<float, float><<<grid, threads, 0, stream>>>(a);
+  else if (out_f32)
+    backward_finish_kernel<__nv_bfloat16, float><<<grid, threads, 0, stream>>>(a);
+  else
+    backward_finish_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, threads, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  if (dt3 != nullptr) {
+    DtArgs d{w.dt_part, t3, g3, dt3, w.lay.row_tiles * w.lay.col_tiles, w.pb.rows_global, grad_mult};
+    dt_finish_kernel<<<3, 1024, 0, stream>>>(d);
+    SCLIP_CUDA_OK(cudaGetLastError());
+  }
+  return SCLIP_OK;
+}
+
+}  // namespace sclip

@@ -1,0 +1,527 @@
+// Tensor-core kernels of the tri-modal contrastive objective (tcgen05 / TMEM / TMA, sm_100a only).
+//
+//   forward_tiles   S = Xhat_rows . Xhat_cols^T per 128x256 tile, epilogue: E = exp(s*S - ref), row sums,
+//                   column sums, diagonal -- the logits never leave TMEM          (model.py:254-265, 52-58)
+//   backward_tiles  recompute S, epilogue: G' = kappa c_p ((softmax_rows + softmax_cols)/2 - I) as fp16 tiles
+//                   + partial sums of dL/dlogit_scale                               (autograd of model.py:52-58)
+//   gemm            dXhat = G' . Xhat_cols,  dXhat += G'^T . Xhat_rows              (autograd of model.py:255,260,265)
+//
+// All three share one mainloop: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer and TMEM owner,
+// warps 2-5 = epilogue (one TMEM lane quarter each).  One 128x256 fp32 accumulator (256 TMEM columns) per CTA,
+// two CTAs per SM so one CTA's epilogue overlaps the other's MMAs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sclip {
+using namespace ptx;
+
+namespace {
+
+struct __align__(8) PipeBarriers {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint8_t* aligned_dyn_smem() {
+  extern __shared__ uint8_t dyn_smem_raw[];
+  uint32_t a = smem_u32(dyn_smem_raw);
+  uint32_t pad = (1024u - (a & 1023u)) & 1023u;
+  return dyn_smem_raw + pad;
+}
+
+// ---------------------------------------------------------------------------------------------- mainloop roles
+__device__ __forceinline__ void producer_loop(const CUtensorMap* maps, const Job& job, int m0, int n0, uint8_t* smem,
+                                              PipeBarriers* bars) {
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int s = 0; s < job.nseg; ++s) {
+    const Segment seg = job.seg[s];
+    const CUtensorMap* ma = maps + seg.map_a;
+    const CUtensorMap* mb = maps + seg.map_b;
+    for (int kb = 0; kb < seg.num_kb; ++kb) {
+      mbar_wait_bounded(&bars->empty[stage], phase ^ 1u, 1);
+      mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+      uint8_t* sa = smem + stage * STAGE_BYTES;
+      uint8_t* sb = sa + A_STAGE_BYTES;
+      const int k = kb * BK;
+      if (!seg.a_mn) {
+        tma_load_2d(sa, ma, &bars->full[stage], k, m0);
+      } else {
+#pragma unroll
+        for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * MN_BOX_BYTES, ma, &bars->full[stage], m0 + g * 64, k);
+      }
+      if (!seg.b_mn) {
+        tma_load_2d(sb, mb, &bars->full[stage], k, n0);
+      } else {
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g) tma_load_2d(sb + g * MN_BOX_BYTES, mb, &bars->full[stage], n0 + g * 64, k);
+      }
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void mma_loop(const Job& job, uint8_t* smem, PipeBarriers* bars, uint32_t tmem_acc) {
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t accumulate = 0;
+  for (int s = 0; s < job.nseg; ++s) {
+    const Segment seg = job.seg[s];
+    const uint32_t idesc = make_idesc_f16(BM, BN, /*fp16*/ 0, seg.a_mn, seg.b_mn);
+    for (int kb = 0; kb < seg.num_kb; ++kb) {
+      mbar_wait_bounded(&bars->full[stage], phase, 2);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+      const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) {
+        // K-major: 8-row groups 1024 B apart, k step = 32 B inside the 128-byte swizzle row.
+        // MN-major: 64-element groups one box (8 KiB) apart, 8-k groups 1024 B apart, k step = 16 rows = 2 KiB.
+        const uint64_t adesc = seg.a_mn ? make_smem_desc_sw128(a_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
+                                        : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
+        const uint64_t bdesc = seg.b_mn ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
+                                        : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
+        umma_f16<1>(tmem_acc, adesc, bdesc, idesc, accumulate);
+        accumulate = 1;
+      }
+      umma_commit_1sm(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  umma_commit_1sm(&bars->tmem_full);  // accumulator complete
+}
+
+// Common prologue: barrier init, TMEM allocation.  Returns the TMEM base address of the 256-column accumulator.
+__device__ __forceinline__ uint32_t tile_setup(PipeBarriers* bars, int warp, int lane) {
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    mbar_init(&bars->tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(&bars->tmem_base, BN);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
+}
+
+__device__ __forceinline__ void tile_teardown(uint32_t tmem_acc, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_acc, BN);
+  }
+}
+
+// grouped rasterisation: consecutive CTAs walk down 16 row tiles before moving to the next column tile, so the
+// ~300 co-resident CTAs share a compact set of operand rows in L2
+__device__ __forceinline__ void decode_tile(int id, int nti, int ntj, int& ti, int& tj) {
+  constexpr int GM = 16;
+  const int per_group = GM * ntj;
+  const int group = id / per_group;
+  const int first = group * GM;
+  const int gm = min(nti - first, GM);
+  const int r = id - group * per_group;
+  ti = first + r % gm;
+  tj = r / gm;
+}
+
+// Reduce-scatter over the 32 lanes of a warp: on entry every lane holds 32 values (one per column of a 32-column
+// chunk, for its own row); on exit lane l holds the sum over the 32 rows of column l.  31 shuffles.
+__device__ __forceinline__ float warp_column_sums(float (&e)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int k = 0; k < w; ++k) {
+      const float send = up ? e[k] : e[k + w];
+      const float keep = up ? e[k + w] : e[k];
+      e[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return e[0];
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, w));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) v += __shfl_xor_sync(0xffffffffu, v, w);
+  return v;
+}
+
+constexpr uint32_t kEpiBarrier = 1;   // named barrier of the 128 epilogue threads
+constexpr uint32_t kEpiThreads = 128;
+
+// ============================================================================================== forward tiles
+__global__ void __launch_bounds__(kTileThreads, 2) forward_tiles_kernel(const __grid_constant__ FwdParams P) {
+  __shared__ PipeBarriers bars;
+  __shared__ float colacc[4][BN];
+  __shared__ float red4[4];
+  uint8_t* smem = aligned_dyn_smem();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.y;
+  int ti, tj;
+  decode_tile(blockIdx.x, P.nti, P.ntj, ti, tj);
+  const int m0 = ti * BM, n0 = tj * BN;
+  const Job& job = P.jobs[p];
+
+  const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int epi_tid = q * 32 + lane;
+    const float s = expf(P.t3[p]);
+    const float c = s * kLog2e * P.acc_scale;  // accumulator -> logit in log2 units
+    const int row = m0 + q * 32 + lane;        // local row
+    const bool row_ok = row < P.rows_local;
+    const bool edge = (m0 + BM > P.rows_local) || (n0 + BN > P.rows_global);
+    const int diag_col = P.row_offset + row - n0;  // tile column holding this row's positive pair
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+
+    mbar_wait_bounded(&bars.tmem_full, 0, 3);
+    tc_fence_after();
+
+    // exponent reference of this tile, in log2 units.  s < 40: the bound |logit| <= s (cosines) is used as a fixed
+    // reference; otherwise the true maximum of the tile is taken in a first pass over TMEM.
+    float ref2 = s * kLog2e;
+    if (!(s < kFastPathMaxScale)) {
+      float mx = -INFINITY;
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const bool ok = !edge || (row_ok && (n0 + ch * 32 + k) < P.rows_global);
+          mx = fmaxf(mx, ok ? __uint_as_float(v[k]) : -INFINITY);
+        }
+      }
+      mx = warp_max(mx);
+      if (lane == 0) red4[q] = mx;
+      named_bar_sync(kEpiBarrier, kEpiThreads);
+      mx = fmaxf(fmaxf(red4[0], red4[1]), fmaxf(red4[2], red4[3]));
+      ref2 = mx * c;
+    }
+
+    float rowsum = 0.f;
+    float dval = 0.f;
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + ch * 32, v);
+      tmem_ld_wait();
+      float e[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) e[k] = ex2_approx(fmaf(__uint_as_float(v[k]), c, -ref2));
+      if (edge) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (!(row_ok && (n0 + ch * 32 + k) < P.rows_global)) e[k] = 0.f;
+      }
+      if ((diag_col >> 5) == ch) {  // at most one chunk per warp (diag_col - lane is warp-uniform)
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if ((diag_col & 31) == k) dval = __uint_as_float(v[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) rowsum += e[k];
+      colacc[q][ch * 32 + lane] = warp_column_sums(e, lane);
+    }
+    if (row_ok) {
+      P.row_part[(static_cast<size_t>(p) * P.ntj + tj) * P.rows_local + row] = rowsum;
+      if (diag_col >= 0 && diag_col < BN) P.diag[static_cast<size_t>(p) * P.rows_local + row] = dval * s * P.acc_scale;
+    }
+    named_bar_sync(kEpiBarrier, kEpiThreads);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cc = epi_tid + h * 128;
+      if (n0 + cc < P.rows_global)
+        P.col_part[(static_cast<size_t>(p) * P.nti + ti) * P.rows_global + n0 + cc] =
+            (colacc[0][cc] + colacc[1][cc]) + (colacc[2][cc] + colacc[3][cc]);
+    }
+    if (epi_tid == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ref2 / kLog2e;
+  }
+  tile_teardown(tmem_acc, warp);
+}
+
+// ============================================================================================== backward tiles
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) backward_tiles_kernel(const __grid_constant__ BwdParams P) {
+  __shared__ PipeBarriers bars;
+  __shared__ float colfac[BN];
+  __shared__ float red4[4];
+  uint8_t* smem = aligned_dyn_smem();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.y;
+  int ti, tj;
+  decode_tile(blockIdx.x, P.nti, P.ntj, ti, tj);
+  const int m0 = ti * BM, n0 = tj * BN;
+  const Job& job = P.jobs[p];
+
+  const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int epi_tid = q * 32 + lane;
+    const float s = expf(P.t3[p]);
+    const float c = s * kLog2e * P.acc_scale;
+    // c_p = s_p g_p / max_q |s_q g_q|
+    float mx = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
+    const float cp = mx > 0.f ? (s * P.g3[p]) / mx : 0.f;
+    const float half_kc = 0.5f * kKappa * cp;
+    const bool fast = s < kFastPathMaxScale;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < P.rows_local;
+    const int diag_col = P.row_offset + row - n0;
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    const bool has_lo = P.store_map_lo[p] >= 0;
+
+    // per-row / per-column softmax normalisers, prepared while the MMAs run
+    const float lse_r = row_ok ? P.lse_row[static_cast<size_t>(p) * P.rows_local + row] : 0.f;
+    const float rowfac = fast ? expf(s - lse_r) : lse_r * kLog2e;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cc = epi_tid + h * 128;
+      const float lse_c = (n0 + cc < P.rows_global) ? P.lse_col[static_cast<size_t>(p) * P.rows_global + n0 + cc] : 0.f;
+      colfac[cc] = fast ? expf(s - lse_c) : lse_c * kLog2e;
+    }
+    named_bar_sync(kEpiBarrier, kEpiThreads);
+
+    mbar_wait_bounded(&bars.tmem_full, 0, 3);
+    tc_fence_after();
+    // all TMA loads have landed and every MMA has completed: the pipeline stages are free to stage the G' tiles.
+    // layout: hi slabs at [0, 32 KiB) (two 16 KiB buffers), lo slabs at [32 KiB, 64 KiB)
+    const float ref2 = s * kLog2e;
+    float dtacc = 0.f;
+    const CUtensorMap* map_hi = &P.maps[P.store_map[p]];
+    const CUtensorMap* map_lo = has_lo ? &P.maps[P.store_map_lo[p]] : nullptr;
+    const int r_in_tile = q * 32 + lane;
+
+    for (int sl = 0; sl < BN / 64; ++sl) {
+      const int b = sl & 1;
+      uint8_t* stage_hi = smem + b * 16384;
+      uint8_t* stage_lo = smem + 32768 + b * 16384;
+      if (sl >= 2) {
+        if (epi_tid == 0) tma_store_wait_read<1>();  // the store issued two slabs ago has finished reading buffer b
+        named_bar_sync(kEpiBarrier, kEpiThreads);
+      }
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        const int ch = sl * 2 + hc;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        float g[32];
+        if (fast) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float a = __uint_as_float(v[k]);
+            const float e = ex2_approx(fmaf(a, c, -ref2));
+            g[k] = (e * (rowfac + colfac[ch * 32 + k])) * half_kc;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float a = __uint_as_float(v[k]);
+            const float l2 = a * c;
+            g[k] = (ex2_approx(l2 - rowfac) + ex2_approx(l2 - colfac[ch * 32 + k])) * half_kc;
+          }
+        }
+        if ((diag_col >> 5) == ch) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if ((diag_col & 31) == k) g[k] -= kKappa * cp;
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) dtacc = fmaf(g[k], __uint_as_float(v[k]), dtacc);
+        // fp16 pack + swizzled staging (128-byte rows, 16-byte chunk index XOR row & 7 == TMA SWIZZLE_128B)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 w;
+          w.x = pack_half2(g[j * 8 + 0], g[j * 8 + 1]);
+          w.y = pack_half2(g[j * 8 + 2], g[j * 8 + 3]);
+          w.z = pack_half2(g[j * 8 + 4], g[j * 8 + 5]);
+          w.w = pack_half2(g[j * 8 + 6], g[j * 8 + 7]);
+          const int chunk16 = hc * 4 + j;
+          const uint32_t off = r_in_tile * 128 + ((chunk16 ^ (r_in_tile & 7)) << 4);
+          *reinterpret_cast<uint4*>(stage_hi + off) = w;
+          if (has_lo) {
+            float lo[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) lo[t] = g[j * 8 + t] - __half2float(__float2half_rn(g[j * 8 + t]));
+            uint4 wl;
+            wl.x = pack_half2(lo[0], lo[1]);
+            wl.y = pack_half2(lo[2], lo[3]);
+            wl.z = pack_half2(lo[4], lo[5]);
+            wl.w = pack_half2(lo[6], lo[7]);
+            *reinterpret_cast<uint4*>(stage_lo + off) = wl;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(kEpiBarrier, kEpiThreads);
+      if (epi_tid == 0 && (n0 + sl * 64) < P.rows_global) {
+        tma_store_2d(map_hi, stage_hi, n0 + sl * 64, m0);
+        if (has_lo) tma_store_2d(map_lo, stage_lo, n0 + sl * 64, m0);
+        tma_store_commit();
+      }
+    }
+    dtacc = warp_sum(dtacc);
+    if (lane == 0) red4[q] = dtacc;
+    named_bar_sync(kEpiBarrier, kEpiThreads);
+    if (epi_tid == 0) {
+      P.dt_part[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ((red4[0] + red4[1]) + (red4[2] + red4[3])) * P.acc_scale;
+      tma_store_wait_all<0>();
+    }
+  }
+  tile_teardown(tmem_acc, warp);
+}
+
+// ============================================================================================== plain GEMM tiles
+__global__ void __launch_bounds__(kTileThreads, 2) gemm_tiles_kernel(const __grid_constant__ GemmParams P) {
+  __shared__ PipeBarriers bars;
+  uint8_t* smem = aligned_dyn_smem();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int j = 0;
+#pragma unroll
+  for (int t = 1; t < kMaxJobs; ++t)
+    if (t < P.njobs && static_cast<int>(blockIdx.x) >= P.jobs[t].tile_base) j = t;
+  const Job& job = P.jobs[j];
+  const int local = blockIdx.x - job.tile_base;
+  const int tn = local % job.n_tiles;  // n fastest: the CTAs sharing an A row panel run together
+  const int tm = local / job.n_tiles;
+  const int m0 = tm * BM, n0 = tn * BN;
+
+  const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
+
+  if (warp == 0) {
+    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars);
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc);
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    float alpha = P.alpha0;
+    if (P.t3 != nullptr) {
+      float mx = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
+      alpha *= mx;
+    }
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < P.m[j];
+    const int ncols = P.n[j];
+    float* out = P.out[j] + static_cast<size_t>(row) * P.ldc[j] + n0;
+    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    mbar_wait_bounded(&bars.tmem_full, 0, 3);
+    tc_fence_after();
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + ch * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const int col = n0 + ch * 32 + k4 * 4;
+          if (col + 3 < ncols) {
+            float4 o;
+            o.x = __uint_as_float(v[k4 * 4 + 0]) * alpha;
+            o.y = __uint_as_float(v[k4 * 4 + 1]) * alpha;
+            o.z = __uint_as_float(v[k4 * 4 + 2]) * alpha;
+            o.w = __uint_as_float(v[k4 * 4 + 3]) * alpha;
+            *reinterpret_cast<float4*>(out + ch * 32 + k4 * 4) = o;
+          }
+        }
+      }
+    }
+  }
+  tile_teardown(tmem_acc, warp);
+}
+
+template <class K>
+int prepare_kernel(K kernel) {
+  static bool done = false;  // per kernel instantiation; attribute is per device but all devices of a process match
+  static int last_dev = -1;
+  int dev = 0;
+  SCLIP_CUDA_OK(cudaGetDevice(&dev));
+  if (!done || dev != last_dev) {
+    SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+    SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    done = true;
+    last_dev = dev;
+  }
+  return SCLIP_OK;
+}
+
+}  // namespace
+
+int launch_forward_tiles(const FwdParams& p, cudaStream_t stream) {
+  int rc = prepare_kernel(forward_tiles_kernel);
+  if (rc) return rc;
+  dim3 grid(p.nti * p.ntj, 3, 1);
+  forward_tiles_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(p);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_backward_tiles(const BwdParams& p, cudaStream_t stream) {
+  int rc = prepare_kernel(backward_tiles_kernel);
+  if (rc) return rc;
+  dim3 grid(p.nti * p.ntj, 3, 1);
+  backward_tiles_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(p);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  int rc = prepare_kernel(gemm_tiles_kernel);
+  if (rc) return rc;
+  dim3 grid(p.total_tiles, 1, 1);
+  gemm_tiles_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(p);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+}  // namespace sclip

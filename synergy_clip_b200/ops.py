@@ -1,0 +1,306 @@
+"""Host side of the fused tri-modal contrastive objective.
+
+``fused_tri_contrastive(img, txt, aud, t_IT, t_TA, t_AI)`` replaces lines 247-272 of the reference
+``Tri_CLIP.forward`` (``/root/reference/model.py``) together with ``clip_loss`` / ``contrastive_loss``
+(``model.py:52-58``): it returns the three 0-dim losses ``(IT_loss, TA_loss, AI_loss)`` and is
+differentiable with respect to the three (un-normalised) embeddings and the three log-temperatures.
+
+PyTorch is plumbing here: device memory (one workspace blob per problem shape), the current CUDA
+stream, autograd wiring and -- when the batch is sharded over ranks -- the NCCL collectives of
+``torch.distributed``.  All arithmetic happens in ``libsclip.so`` (``include/sclip.h``); there is
+no CPU or eager fallback, and a missing library or a failed call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from ctypes import byref
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MATH_F16, MATH_F16X3, Problem, SCLIP_BF16, SCLIP_F32
+
+__all__ = ["fused_tri_contrastive", "TriContrastiveConfig", "gemm_f16", "workspace_bytes"]
+
+
+class TriContrastiveConfig:
+    """Knobs that do not exist in the reference (defaults reproduce it: local batch, no collectives).
+
+    process_group : shard the *global* batch over the ranks of this group (row strips); ``None`` keeps the
+                    reference behaviour (each rank's loss uses its local batch only, model.py:248-272).
+    math          : "f16" (fp16 tensor-core operands, fp32 accumulate), "f16x3" (split operands, ~fp32
+                    accuracy at 3x the tensor-core work) or "auto" (f16x3 for fp32 inputs, f16 for bf16).
+    grad_scale    : "ddp"  -> gradients are multiplied by world_size because the caller's DDP wrapper averages
+                              parameter gradients over ranks (main_pretraining.py:138);
+                    "sum"  -> exact partial derivatives of the global-batch losses.
+    grads_fp32    : emit fp32 embedding gradients even for bf16 inputs (used by the parity tests).
+    """
+
+    def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False):
+        if math not in ("auto", "f16", "f16x3"):
+            raise ValueError(f"math={math!r}")
+        if grad_scale not in ("ddp", "sum"):
+            raise ValueError(f"grad_scale={grad_scale!r}")
+        self.process_group = process_group
+        self.math = math
+        self.grad_scale = grad_scale
+        self.grads_fp32 = grads_fp32
+
+
+_DEFAULT = TriContrastiveConfig()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _Workspace:
+    """One workspace blob + typed views of the sub-buffers the host touches."""
+
+    def __init__(self, pb: Problem, device: torch.device):
+        self.pb = pb
+        self.lay = _lib.plan(pb)
+        self.blob = torch.empty(int(self.lay.total_bytes), dtype=torch.uint8, device=device)
+        if self.blob.data_ptr() % 256:
+            raise _lib.SclipError("allocator returned a workspace that is not 256-byte aligned")
+
+    def view(self, offset: int, shape, dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        return self.blob[int(offset):int(offset) + nbytes].view(dtype).view(*shape)
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.blob.data_ptr())
+
+
+class _Pool:
+    """Workspaces are recycled per problem shape; one is held from forward until its backward has run."""
+
+    def __init__(self):
+        self._free = {}
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _key(pb: Problem, device):
+        return (device.index, pb.rows_local, pb.rows_global, pb.row_offset, pb.dim, pb.dtype, pb.math, pb.world)
+
+    def acquire(self, pb: Problem, device) -> _Workspace:
+        with self._lock:
+            lst = self._free.get(self._key(pb, device))
+            if lst:
+                return lst.pop()
+        return _Workspace(pb, device)
+
+    def release(self, ws: _Workspace):
+        with self._lock:
+            self._free.setdefault(self._key(ws.pb, ws.blob.device), []).append(ws)
+
+    def clear(self):
+        with self._lock:
+            self._free.clear()
+
+
+_POOL = _Pool()
+
+
+class _Lease:
+    def __init__(self, ws: _Workspace):
+        self.ws = ws
+
+    def __del__(self):
+        ws, self.ws = self.ws, None
+        if ws is not None:
+            try:
+                _POOL.release(ws)
+            except Exception:
+                pass
+
+
+def _make_problem(img: torch.Tensor, cfg: TriContrastiveConfig) -> Tuple[Problem, int, int]:
+    import torch.distributed as dist
+
+    rows, dim = img.shape
+    world, rank = 1, 0
+    if cfg.process_group is not None:
+        world = dist.get_world_size(cfg.process_group)
+        rank = dist.get_rank(cfg.process_group)
+    if img.dtype == torch.float32:
+        dtype = SCLIP_F32
+    elif img.dtype == torch.bfloat16:
+        dtype = SCLIP_BF16
+    else:
+        raise TypeError(f"embeddings must be float32 or bfloat16, got {img.dtype}")
+    math = cfg.math
+    if math == "auto":
+        math = "f16x3" if dtype == SCLIP_F32 else "f16"
+    pb = Problem(rows_local=rows, rows_global=rows * world, row_offset=rows * rank, dim=dim, dtype=dtype,
+                 math=MATH_F16X3 if math == "f16x3" else MATH_F16, world=world, reserved=0)
+    return pb, world, rank
+
+
+def workspace_bytes(rows_local: int, dim: int, dtype=torch.bfloat16, world: int = 1, math: str = "auto") -> int:
+    """Size of the workspace the library needs for a problem (pure host arithmetic, no GPU needed)."""
+    d = SCLIP_F32 if dtype == torch.float32 else SCLIP_BF16
+    if math == "auto":
+        math = "f16x3" if d == SCLIP_F32 else "f16"
+    pb = Problem(rows_local, rows_local * world, 0, dim, d, MATH_F16X3 if math == "f16x3" else MATH_F16, world, 0)
+    return int(_lib.plan(pb).total_bytes)
+
+
+def _check_inputs(img, txt, aud):
+    for name, e in (("image", img), ("text", txt), ("audio", aud)):
+        if not e.is_cuda:
+            raise _lib.SclipError(
+                f"{name} embeddings are on {e.device}: the fused contrastive objective only runs on a CUDA (sm_100a) "
+                "device and has no CPU fallback")
+        if e.dim() != 2 or e.shape != img.shape or e.dtype != img.dtype or e.device != img.device:
+            raise ValueError("image / text / audio embeddings must share one (B, D) shape, dtype and device")
+
+
+def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) -> torch.Tensor:
+    lib = _lib.load()
+    pb, lay, st = ws.pb, ws.lay, _stream()
+    _lib.check(lib.sclip_prologue(byref(pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), st), "sclip_prologue")
+    loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
+    if pb.world == 1:
+        _lib.check(lib.sclip_forward_tiles(byref(pb), ws.ptr, _ptr(t3), st), "sclip_forward_tiles")
+        _lib.check(lib.sclip_forward_reduce(byref(pb), ws.ptr, st), "sclip_forward_reduce")
+        _lib.check(lib.sclip_forward_loss(byref(pb), ws.ptr, None, _ptr(loss3), st), "sclip_forward_loss")
+        return loss3
+    import torch.distributed as dist
+
+    pg = cfg.process_group
+    bl, bg, d, off = pb.rows_local, pb.rows_global, pb.dim, pb.row_offset
+    bufs = [ws.view(lay.xhat, (3, bg, d), torch.float16)]
+    if pb.math == MATH_F16X3:
+        bufs.append(ws.view(lay.xhat_lo, (3, bg, d), torch.float16))
+    for buf in bufs:  # all-gather of the normalised row shards (each modality is column-side in one pair)
+        for m in range(3):
+            dist.all_gather_into_tensor(buf[m], buf[m, off:off + bl], group=pg)
+    _lib.check(lib.sclip_forward_tiles(byref(pb), ws.ptr, _ptr(t3), st), "sclip_forward_tiles")
+    _lib.check(lib.sclip_forward_reduce(byref(pb), ws.ptr, st), "sclip_forward_reduce")
+    col_local = ws.view(lay.lse_col_local, (3, bg), torch.float32)
+    col_all = torch.empty((pb.world, 3, bg), dtype=torch.float32, device=img.device)
+    dist.all_gather_into_tensor(col_all, col_local, group=pg)
+    _lib.check(lib.sclip_forward_loss(byref(pb), ws.ptr, _ptr(col_all), _ptr(loss3), st), "sclip_forward_loss")
+    dist.all_reduce(loss3, group=pg)  # every rank reports the global-batch losses
+    return loss3
+
+
+def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveConfig):
+    lib = _lib.load()
+    pb, lay, st = ws.pb, ws.lay, _stream()
+    out_f32 = 1 if (cfg.grads_fp32 or img.dtype == torch.float32) else 0
+    gdtype = torch.float32 if out_f32 else img.dtype
+    dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
+    dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
+    _lib.check(lib.sclip_backward_tiles(byref(pb), ws.ptr, _ptr(t3), _ptr(g3), st), "sclip_backward_tiles")
+    _lib.check(lib.sclip_backward_gemms(byref(pb), ws.ptr, _ptr(t3), _ptr(g3), st), "sclip_backward_gemms")
+    col = None
+    mult = 1.0
+    if pb.world > 1:
+        import torch.distributed as dist
+
+        bl, bg, d = pb.rows_local, pb.rows_global, pb.dim
+        part = ws.view(lay.dxhat_col, (3, bg, d), torch.float32)
+        col = torch.empty((3, bl, d), dtype=torch.float32, device=img.device)
+        for m in range(3):  # reduce-scatter of the column-role partial gradients
+            dist.reduce_scatter_tensor(col[m], part[m], group=cfg.process_group)
+        if cfg.grad_scale == "ddp":
+            mult = float(pb.world)
+    _lib.check(
+        lib.sclip_backward_finish(byref(pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3), _ptr(g3), _ptr(col),
+                                  ctypes.c_float(mult), _ptr(dimg), _ptr(dtxt), _ptr(daud), out_f32, _ptr(dt3), st),
+        "sclip_backward_finish")
+    if pb.world > 1 and cfg.grad_scale == "sum":
+        import torch.distributed as dist
+
+        dist.all_reduce(dt3, group=cfg.process_group)
+    return dimg, dtxt, daud, dt3
+
+
+class _TriContrastive(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, txt, aud, t3, cfg):
+        img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
+        pb, _, _ = _make_problem(img, cfg)
+        ws = _POOL.acquire(pb, img.device)
+        lease = _Lease(ws)
+        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg)
+        ctx.save_for_backward(img, txt, aud, t3)
+        ctx.lease = lease
+        ctx.cfg = cfg
+        return loss3
+
+    @staticmethod
+    def backward(ctx, g3):
+        img, txt, aud, t3 = ctx.saved_tensors
+        ws = ctx.lease.ws
+        g3 = g3.to(torch.float32).contiguous()
+        dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, ctx.cfg)
+        if not ctx.cfg.grads_fp32:
+            dimg, dtxt, daud = dimg.to(img.dtype), dtxt.to(img.dtype), daud.to(img.dtype)
+        return dimg, dtxt, daud, dt3, None
+
+
+def fused_tri_contrastive(img: torch.Tensor, txt: torch.Tensor, aud: torch.Tensor, t_IT: torch.Tensor,
+                          t_TA: torch.Tensor, t_AI: torch.Tensor, config: Optional[TriContrastiveConfig] = None):
+    """(IT_loss, TA_loss, AI_loss) of model.py:247-272 for (B, D) projection outputs and the three
+    ``logit_scale_for_*`` parameters (0-dim fp32, model.py:80-82)."""
+    cfg = config or _DEFAULT
+    _check_inputs(img, txt, aud)
+    t3 = torch.stack([t_IT.reshape(()), t_TA.reshape(()), t_AI.reshape(())]).to(device=img.device, dtype=torch.float32)
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (img, txt, aud, t_IT, t_TA, t_AI))
+    if needs_grad:
+        loss3 = _TriContrastive.apply(img, txt, aud, t3, cfg)
+    else:  # eval loops run under torch.no_grad() (main_pretraining.py:192-210): nothing is kept for backward
+        img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
+        pb, _, _ = _make_problem(img, cfg)
+        ws = _POOL.acquire(pb, img.device)
+        try:
+            loss3 = _forward_impl(ws, img.detach(), txt.detach(), aud.detach(), t3.detach(), cfg)
+        finally:
+            _POOL.release(ws)
+    return loss3[0], loss3[1], loss3[2]
+
+
+def forward_backward_raw(img, txt, aud, t3, g3, config: Optional[TriContrastiveConfig] = None):
+    """One fwd+bwd without autograd bookkeeping (bench / tests): returns (loss3, dimg, dtxt, daud, dt3)."""
+    cfg = config or _DEFAULT
+    _check_inputs(img, txt, aud)
+    pb, _, _ = _make_problem(img, cfg)
+    ws = _POOL.acquire(pb, img.device)
+    try:
+        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg)
+        dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, cfg)
+    finally:
+        _POOL.release(ws)
+    return loss3, dimg, dtxt, daud, dt3
+
+
+def gemm_f16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, alpha: float = 1.0):
+    """C = alpha * A @ B^T-style contraction on the tcgen05 tile kernel (tests, zero-shot scorers).
+
+    a_mn=False: ``a`` is (M, K); a_mn=True: ``a`` is (K, M).  b_mn=False: ``b`` is (N, K); b_mn=True: ``b`` is (K, N).
+    """
+    lib = _lib.load()
+    if a.dtype != torch.float16 or b.dtype != torch.float16 or not a.is_cuda:
+        raise TypeError("gemm_f16 takes CUDA float16 operands")
+    a, b = a.contiguous(), b.contiguous()
+    m, k = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    n, kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if k != kb:
+        raise ValueError("inner dimensions differ")
+    c = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    _lib.check(lib.sclip_gemm_f16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(c), n, m, n, k,
+                                  ctypes.c_float(alpha), _stream()), "sclip_gemm_f16")
+    return c

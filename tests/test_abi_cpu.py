@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds/loads, exports every symbol include/sclip.h declares, and its host-only entry
+points (sclip_plan, argument validation) behave.  No compute calls are made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from synergy_clip_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sclip.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sclip_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 13
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_lib.EXPORTS)
+    assert lib.sclip_abi_version() == 1
+
+
+def test_plan_layout_is_consistent():
+    pb = _lib.Problem(4096, 32768, 8192, 768, _lib.SCLIP_BF16, _lib.MATH_F16, 8, 0)
+    lay = _lib.plan(pb)
+    assert lay.row_tiles == 32 and lay.col_tiles == 128 and lay.ld_g == 32768
+    offs = [getattr(lay, f) for f, _ in _lib.Layout._fields_[1:18]]
+    assert all(o % 256 == 0 for o in offs)
+    assert lay.total_bytes > 3 * 4096 * 32768 * 2  # the three G' strips dominate
+    assert lay.dxhat_col != lay.dxhat_row
+    single = _lib.plan(_lib.Problem(256, 256, 0, 512, _lib.SCLIP_F32, _lib.MATH_F16X3, 1, 0))
+    assert single.dxhat_col == single.dxhat_row and single.xhat_lo != single.xhat
+
+
+@pytest.mark.parametrize("bad", [
+    dict(rows_local=0), dict(dim=100), dict(dtype=7), dict(math=5), dict(world=0),
+    dict(rows_local=128, rows_global=64), dict(row_offset=200),
+])
+def test_plan_rejects_bad_problems(bad):
+    kw = dict(rows_local=128, rows_global=128, row_offset=0, dim=512, dtype=0, math=0, world=1, reserved=0)
+    kw.update(bad)
+    lay = _lib.Layout()
+    rc = _lib.load().sclip_plan(ctypes.byref(_lib.Problem(**kw)), ctypes.byref(lay))
+    assert rc == -1
+    assert len(_lib.load().sclip_last_error()) > 0
+
+
+def test_null_arguments_are_errors_not_crashes():
+    lib = _lib.load()
+    assert lib.sclip_plan(None, None) == -1
+    pb = _lib.Problem(128, 128, 0, 512, 0, 0, 1, 0)
+    assert lib.sclip_forward_tiles(ctypes.byref(pb), None, None, None) == -1
+    assert lib.sclip_gemm_f16(None, 0, 0, None, 0, 0, None, 0, 1, 4, 1, 1.0, None) == -1
+
+
+def test_op_refuses_cpu_tensors():
+    import torch
+
+    from synergy_clip_b200 import fused_tri_contrastive
+
+    x = torch.randn(8, 16)
+    t = torch.tensor(2.6592)
+    with pytest.raises(_lib.SclipError):
+        fused_tri_contrastive(x, x, x, t, t, t)

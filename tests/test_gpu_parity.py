@@ -1,0 +1,127 @@
+"""GPU: the CUDA path (through the C ABI) against the reference-generated golden vectors and the numpy oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form
+from tests import golden_util
+
+pytestmark = pytest.mark.gpu
+
+# tolerances from BASELINE.json north_star: 1e-3 relative for the bf16 / fp16-operand mode, 1e-5 for fp32
+TOL_F16 = 1e-3
+TOL_F32 = 1e-5
+
+
+def _run(embs, t3, g3, dtype, math_mode):
+    from synergy_clip_b200 import ops
+
+    dev = torch.device("cuda")
+    ten = [torch.from_numpy(np.ascontiguousarray(e)).to(dev).to(dtype) for e in embs]
+    t3d = torch.tensor(t3, dtype=torch.float32, device=dev)
+    g3d = torch.tensor(g3, dtype=torch.float32, device=dev)
+    cfg = ops.TriContrastiveConfig(math=math_mode, grads_fp32=True)
+    loss3, dimg, dtxt, daud, dt3 = ops.forward_backward_raw(*ten, t3d, g3d, cfg)
+    torch.cuda.synchronize()
+    return {"loss": loss3.double().cpu().numpy(), "dscale": dt3.double().cpu().numpy(),
+            "dimg": dimg.double().cpu().numpy(), "dtxt": dtxt.double().cpu().numpy(),
+            "daud": daud.double().cpu().numpy()}
+
+
+@pytest.mark.parametrize("name", golden_util.case_names())
+def test_golden_f16_operands(name):
+    meta, embs, data = golden_util.load_case(name)
+    dtype = torch.bfloat16 if meta["bf16_inputs"] else torch.float32
+    res = _run(embs, meta["t3"], meta["g3"], dtype, "f16")
+    errs = golden_util.golden_errors(meta, data, res)
+    assert max(errs.values()) < TOL_F16, errs
+
+
+@pytest.mark.parametrize("name", [n for n in golden_util.case_names() if not golden_util.load_case(n)[0]["bf16_inputs"]])
+def test_golden_fp32_split_operands(name):
+    meta, embs, data = golden_util.load_case(name)
+    res = _run(embs, meta["t3"], meta["g3"], torch.float32, "f16x3")
+    errs = golden_util.golden_errors(meta, data, res)
+    assert max(errs.values()) < TOL_F32, errs
+
+
+def test_autograd_matches_oracle_and_respects_weights():
+    from synergy_clip_b200 import fused_tri_contrastive
+
+    embs = closed_form.synthetic_embeddings(200, 256, 77, 0.2)
+    t3, w3 = (2.6592, 2.9, 2.2), (0.3, 0.7, 1.1)
+    want = closed_form.tri_contrastive(*embs, t3, w3)
+    ten = [torch.from_numpy(e).cuda().requires_grad_(True) for e in embs]
+    ts = [torch.tensor(t, device="cuda", requires_grad=True) for t in t3]
+    it, ta, ai = fused_tri_contrastive(*ten, *ts)
+    assert it.dim() == 0 and it.dtype == torch.float32
+    (w3[0] * it + w3[1] * ta + w3[2] * ai).backward()  # main_pretraining.py:166-173
+    got_loss = np.array([it.item(), ta.item(), ai.item()])
+    assert np.max(np.abs(got_loss - want["loss"]) / want["loss"]) < TOL_F32
+    for t, key in zip(ten, ("dimg", "dtxt", "daud")):
+        assert golden_util.rel(t.grad.cpu().numpy(), want[key]) < TOL_F32, key
+    got_dt = np.array([t.grad.item() for t in ts])
+    assert np.max(np.abs(got_dt - want["dscale"]) / np.abs(want["dscale"])) < TOL_F32
+
+
+def test_no_grad_forward_only():
+    from synergy_clip_b200 import fused_tri_contrastive
+
+    embs = closed_form.synthetic_embeddings(100, 128, 5)
+    want = closed_form.tri_contrastive(*embs, (2.6592,) * 3, want_grads=False)
+    ten = [torch.from_numpy(e).cuda().requires_grad_(True) for e in embs]
+    t = torch.tensor(2.6592, device="cuda", requires_grad=True)
+    with torch.no_grad():
+        out = fused_tri_contrastive(*ten, t, t, t)
+    assert all(not o.requires_grad for o in out)
+    assert np.max(np.abs(np.array([o.item() for o in out]) - want["loss"]) / want["loss"]) < TOL_F32
+
+
+def test_bf16_output_is_rounding_of_fp32_emission():
+    from synergy_clip_b200 import ops
+
+    embs = [closed_form.round_to_bf16(e) for e in closed_form.synthetic_embeddings(300, 512, 9)]
+    ten = [torch.from_numpy(e).cuda().bfloat16() for e in embs]
+    t3 = torch.full((3,), 2.6592, device="cuda")
+    g3 = torch.ones(3, device="cuda")
+    f32 = ops.forward_backward_raw(*ten, t3, g3, ops.TriContrastiveConfig(math="f16", grads_fp32=True))
+    b16 = ops.forward_backward_raw(*ten, t3, g3, ops.TriContrastiveConfig(math="f16", grads_fp32=False))
+    for a, b in zip(f32[1:4], b16[1:4]):
+        assert b.dtype == torch.bfloat16 and torch.equal(a.bfloat16(), b)
+
+
+def test_large_scale_properties_full_size():
+    """BASELINE config 2 (B=8192, D=512, bf16): size-independent properties instead of an O(B^2) oracle run."""
+    from synergy_clip_b200 import ops
+
+    b, d = 8192, 512
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    ten = [torch.randn(b, d, device="cuda", generator=g).bfloat16() for _ in range(3)]
+    t3 = torch.full((3,), 2.6592, device="cuda")
+    g3 = torch.tensor([0.25, 0.5, 0.125], device="cuda")
+    cfg = ops.TriContrastiveConfig(math="f16", grads_fp32=True)
+    loss, dimg, dtxt, daud, dt = ops.forward_backward_raw(*ten, t3, g3, cfg)
+    loss2, dimg2, _, _, dt2 = ops.forward_backward_raw(*ten, t3, g3, cfg)
+    assert torch.equal(loss, loss2) and torch.equal(dimg, dimg2) and torch.equal(dt, dt2)  # deterministic
+    # random unit vectors: loss slightly above ln B
+    assert all(math.log(b) < v < math.log(b) + 0.5 for v in loss.tolist())
+    # the loss depends on x only through x/||x||: the gradient is orthogonal to x, and scaling x by c scales it by 1/c
+    for x, gx in zip(ten, (dimg, dtxt, daud)):
+        dots = (x.float() * gx).sum(-1)
+        assert dots.abs().max().item() < 1e-3 * gx.norm(dim=-1).max().item() * x.float().norm(dim=-1).max().item()
+    scaled = [ten[0] * 2, ten[1], ten[2]]
+    loss_s, dimg_s, dtxt_s, _, _ = ops.forward_backward_raw(*scaled, t3, g3, cfg)
+    assert torch.allclose(loss_s, loss, rtol=1e-6, atol=0)
+    assert torch.allclose(dimg_s * 2, dimg, rtol=1e-4, atol=1e-9)
+    # linearity in the upstream gradients
+    _, dimg_h, _, _, dt_h = ops.forward_backward_raw(*ten, t3, g3 * 0.5, cfg)
+    assert torch.allclose(dimg_h * 2, dimg, rtol=1e-5, atol=1e-10)
+    assert torch.allclose(dt_h * 2, dt, rtol=1e-5, atol=0)
+    # sub-sampled oracle check: rows 0..255 of the image gradient need the full column statistics, so compare
+    # the loss of a 1024-sample sub-batch instead
+    sub = [t[:1024] for t in ten]
+    want = closed_form.tri_contrastive(*[s.float().cpu().numpy() for s in sub], (2.6592,) * 3, want_grads=False)
+    got = ops.forward_backward_raw(*[s.contiguous() for s in sub], t3, g3, cfg)[0]
+    assert np.max(np.abs(got.cpu().numpy() - want["loss"]) / want["loss"]) < TOL_F16

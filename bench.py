@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the fused tri-modal contrastive objective (BASELINE.json metric: fwd+bwd samples/s, % of
+tensor-core peak).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's PyTorch CPU loss path (oracle port)
+
+One "step" = one forward + backward of the loss tail (model.py:247-272 + autograd) over one synthetic global
+batch.  Workload (every N, strong scaling): the north-star shape B=32768, D=768, bf16 embeddings, row-sharded
+over the N ranks.  The BASELINE config-2 shape (8192 x 512, single GPU) is timed in the same run and reported
+under "also".  Prints exactly one JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOGIT_SCALE_INIT = 2.6592  # config.py:112
+WORKLOADS = {"north_star": (32768, 768), "cfg2": (8192, 512)}
+CPU_SAMPLE_ROWS = 4096  # bounded CPU sample: a 4096-row sub-batch of the same embeddings
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), start=3):
+            if any(s[i].lower() == "active" for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+def cpu_tail_rate(rows: int, dim: int, steps: int, warmup: int, seed: int = 1234):
+    """The reference's PyTorch CPU loss path (oracle/reference_tail.py restates model.py:247-272 verbatim) in fp32
+    on all host cores: returns (samples/s, seconds per step, threads)."""
+    import torch
+
+    from oracle import reference_tail
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    leaves = [torch.randn(rows, dim, generator=g).requires_grad_(True) for _ in range(3)]
+    scales = [torch.tensor(LOGIT_SCALE_INIT, requires_grad=True) for _ in range(3)]
+    for _ in range(warmup):
+        reference_tail.timed_step(*leaves, scales)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        reference_tail.timed_step(*leaves, scales)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return rows / dt, dt, threads
+
+
+def cpu_full_batch_rate(rows: int, b: int, dt: float) -> float:
+    """The work of the tail is quadratic in the batch (3 BxB similarity matrices): a step over the full batch of b
+    samples costs (b / rows)^2 sub-batch steps, so the whole-job rate on the full workload is b / (dt (b/rows)^2)."""
+    return b / (dt * (b / rows) ** 2)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    b, d = WORKLOADS[args.workload]
+    rows = min(CPU_SAMPLE_ROWS, b)
+    sub_rate, dt, threads = cpu_tail_rate(rows, d, args.steps, args.warmup)
+    rate = cpu_full_batch_rate(rows, b, dt)
+    sample = (f"each step = fwd+bwd of a {rows}-row sub-batch of the {b}x{d} workload (fp32, torch CPU, {threads} "
+              f"threads, {dt:.2f} s/step = {sub_rate:.0f} samples/s at B={rows}); value is that time scaled by the "
+              f"quadratic work ratio (B/{rows})^2 to the full batch, which itself needs 9 BxB fp32 matrices")
+    line = {
+        "impl": "reference", "metric": "contrastive_loss_fwd_bwd_samples_per_sec", "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"tri-modal contrastive loss fwd+bwd, global batch {b}, dim {d}", "rows_global": b,
+                   "dim": d, "reference_sample_rows": rows},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def time_steps(fn, steps, warmup, dist_mod=None):
+    """W warm-up + K timed calls of fn, CUDA events on the current stream, barrier + synchronize on both sides,
+    max over ranks.  Returns ms per step."""
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if dist_mod is not None:
+        dist_mod.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_mod is not None:
+        dist_mod.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist_mod is not None:
+        dist_mod.all_reduce(ms, op=dist_mod.ReduceOp.MAX)
+    return ms.item() / steps
+
+
+def stage_breakdown(run, steps):
+    """Average device time of every stage (CUDA events recorded between the stage launches of `run`)."""
+    import torch
+
+    from synergy_clip_b200 import ops
+
+    acc = {}
+    for _ in range(steps):
+        marks = []
+
+        def trace(name, marks=marks):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+        ops._TRACE = trace
+        try:
+            run()
+        finally:
+            ops._TRACE = None
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            if name in ("begin", "backward_begin"):
+                continue
+            acc.setdefault(name, []).append(a.elapsed_time(b))
+    return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from synergy_clip_b200 import fused_tri_contrastive, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    peaks = load_peaks()
+
+    def make_inputs(b, d, shard):
+        g = torch.Generator(device=dev).manual_seed(1234)
+        full = [torch.randn(b, d, device=dev, generator=g).to(torch.bfloat16) for _ in range(3)]
+        if shard and world > 1:
+            bl = b // world
+            full = [f[rank * bl:(rank + 1) * bl].contiguous() for f in full]
+        return full
+
+    def measure(b, d, shard, steps, warmup):
+        cfg = ops.TriContrastiveConfig(process_group=pg if shard else None, math="f16", grad_scale="ddp")
+        embs = make_inputs(b, d, shard)
+        t3 = torch.full((3,), LOGIT_SCALE_INIT, device=dev)
+        g3 = torch.ones(3, device=dev)
+        out = {}
+
+        def resident_step():
+            out["r"] = ops.forward_backward_raw(*embs, t3, g3, cfg)
+
+        sampler = ClockSampler(local_rank)
+        with sampler:
+            ms = time_steps(resident_step, steps, warmup, dist if shard else None)
+        stages = stage_breakdown(resident_step, min(steps, 5))
+
+        # end to end through the public autograd API with HOST buffers
+        host = [e.cpu().pin_memory() for e in embs]
+        dbuf = [torch.empty_like(e) for e in embs]
+        params = [torch.full((), LOGIT_SCALE_INIT, device=dev, requires_grad=True) for _ in range(3)]
+        loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            leaves = []
+            for h, dst in zip(host, dbuf):
+                dst.copy_(h, non_blocking=True)
+                leaves.append(dst.detach().requires_grad_(True))
+            for p in params:
+                p.grad = None
+            it, ta, ai = fused_tri_contrastive(*leaves, *params, config=cfg)
+            (it + ta + ai).backward()
+            loss_host.copy_(torch.stack([it.detach(), ta.detach(), ai.detach()]), non_blocking=True)
+            torch.cuda.current_stream().synchronize()  # the caller reads the losses (main_pretraining.py:169-170)
+
+        ms_e2e = time_steps(e2e_step, steps, warmup, dist if shard else None)
+        h2d = sum(h.numel() * h.element_size() for h in host)
+        return {"ms": ms, "ms_e2e": ms_e2e, "stages": stages, "clocks": sampler.summary(), "h2d": h2d,
+                "loss": [float(x) for x in out["r"][0].tolist()], "rows_local": embs[0].shape[0]}
+
+    b, d = WORKLOADS[args.workload]
+    main_res = measure(b, d, True, args.steps, args.warmup)
+    flops = 18.0 * b * b * d
+    value = b / (main_res["ms"] * 1e-3)
+    tflops_per_gpu = flops / world / (main_res["ms"] * 1e-3) / 1e12
+    # dominant kernel: the gradient GEMM launch (6 of the 9 contractions = 12 B^2 D / world flops per launch)
+    gemm_ms = main_res["stages"].get("backward_gemms")
+    gemm_tf = 12.0 * b * b * d / world / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
+    stage_tf = {}
+    for name, fl in (("forward_tiles", 6.0), ("backward_tiles", 6.0), ("backward_gemms", 12.0)):
+        if main_res["stages"].get(name):
+            stage_tf[name] = fl * b * b * d / world / (main_res["stages"][name] * 1e-3) / 1e12
+
+    also = None
+    if not args.no_also and args.workload == "north_star" and rank == 0 and world == 1:
+        b2, d2 = WORKLOADS["cfg2"]
+        r2 = measure(b2, d2, False, max(args.steps, 20), args.warmup)
+        also = {"cfg2_8192x512_bf16_1gpu": {
+            "value": b2 / (r2["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": r2["ms"],
+            "tflops_algorithmic": 18.0 * b2 * b2 * d2 / (r2["ms"] * 1e-3) / 1e12,
+            "frac_of_bf16_peak": 18.0 * b2 * b2 * d2 / (r2["ms"] * 1e-3) / 1e12 / peaks["bf16_tflops"],
+            "e2e_value": b2 / (r2["ms_e2e"] * 1e-3), "stages_ms": r2["stages"]}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = min(CPU_SAMPLE_ROWS, b)
+        sub_rate, dt, threads = cpu_tail_rate(rows, d, steps=3, warmup=1)
+        cpu = {"value": cpu_full_batch_rate(rows, b, dt), "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{rows}-row sub-batch of the {b}x{d} workload, fp32 torch CPU, 1 warm-up + 3 timed steps "
+                         f"({dt:.2f} s/step = {sub_rate:.0f} samples/s at B={rows}), scaled by the quadratic work "
+                         f"ratio (B/{rows})^2 to the full batch"}
+
+    if rank == 0:
+        line = {
+            "metric": "contrastive_loss_fwd_bwd_samples_per_sec", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": f"tri-modal contrastive loss fwd+bwd, global batch {b}, dim {d}, bf16 embeddings "
+                                   f"in / bf16 gradients out, fp16 tensor-core operands with fp32 accumulation",
+                       "rows_global": b, "rows_per_gpu": main_res["rows_local"], "dim": d,
+                       "parallelism": f"row-strip dp{world}",
+                       "l2": "no explicit flush: each step streams the 3 G' strips (2*B*B/world bytes each) through "
+                             "HBM, far larger than the 126 MB L2"},
+            "tflops_algorithmic_per_gpu": tflops_per_gpu,
+            "frac_of_bf16_peak_per_gpu": tflops_per_gpu / peaks["bf16_tflops"],
+            "clocks": main_res["clocks"],
+            "e2e": {"value": b / (main_res["ms_e2e"] * 1e-3), "unit": "samples/s", "ms_per_step": main_res["ms_e2e"],
+                    "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": 12},
+            "gpu_launches": 8 * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tiles_kernel (backward_gemms)", "achieved": gemm_tf,
+                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": (gemm_tf / peaks["bf16_tflops"]) if gemm_tf else None, "traffic": None,
+                         "peak_source": peaks["source"] + ", burst figure",
+                         "stage_ms": main_res["stages"], "stage_tflops": stage_tf},
+            "cpu_baseline": cpu,
+            "loss": main_res["loss"],
+        }
+        if also:
+            line["also"] = also
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -56,4 +56,4 @@ def timed_step(img, txt, aud, scales):
         p.grad = None
     it, ta, ai = tail_losses(img, txt, aud, *scales)
     (it + ta + ai).backward()
-    return float(it) + float(ta) + float(ai)
+    return float(it.detach()) + float(ta.detach()) + float(ai.detach())

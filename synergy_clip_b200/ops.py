@@ -51,6 +51,14 @@ class TriContrastiveConfig:
 
 _DEFAULT = TriContrastiveConfig()
 
+# Optional stage tracer (bench.py / profiling only): a callable(stage_name) invoked after every stage launch.
+_TRACE = None
+
+
+def _mark(name: str) -> None:
+    if _TRACE is not None:
+        _TRACE(name)
+
 
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -169,12 +177,16 @@ def _check_inputs(img, txt, aud):
 def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) -> torch.Tensor:
     lib = _lib.load()
     pb, lay, st = ws.pb, ws.lay, _stream()
+    _mark("begin")
     _lib.check(lib.sclip_prologue(byref(pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), st), "sclip_prologue")
+    _mark("prologue")
     loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
     if pb.world == 1:
         _lib.check(lib.sclip_forward_tiles(byref(pb), ws.ptr, _ptr(t3), st), "sclip_forward_tiles")
+        _mark("forward_tiles")
         _lib.check(lib.sclip_forward_reduce(byref(pb), ws.ptr, st), "sclip_forward_reduce")
         _lib.check(lib.sclip_forward_loss(byref(pb), ws.ptr, None, _ptr(loss3), st), "sclip_forward_loss")
+        _mark("forward_finish")
         return loss3
     import torch.distributed as dist
 
@@ -186,13 +198,16 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) 
     for buf in bufs:  # all-gather of the normalised row shards (each modality is column-side in one pair)
         for m in range(3):
             dist.all_gather_into_tensor(buf[m], buf[m, off:off + bl], group=pg)
+    _mark("all_gather")
     _lib.check(lib.sclip_forward_tiles(byref(pb), ws.ptr, _ptr(t3), st), "sclip_forward_tiles")
+    _mark("forward_tiles")
     _lib.check(lib.sclip_forward_reduce(byref(pb), ws.ptr, st), "sclip_forward_reduce")
     col_local = ws.view(lay.lse_col_local, (3, bg), torch.float32)
     col_all = torch.empty((pb.world, 3, bg), dtype=torch.float32, device=img.device)
     dist.all_gather_into_tensor(col_all, col_local, group=pg)
     _lib.check(lib.sclip_forward_loss(byref(pb), ws.ptr, _ptr(col_all), _ptr(loss3), st), "sclip_forward_loss")
     dist.all_reduce(loss3, group=pg)  # every rank reports the global-batch losses
+    _mark("forward_finish")
     return loss3
 
 
@@ -203,8 +218,11 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     gdtype = torch.float32 if out_f32 else img.dtype
     dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
     dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
+    _mark("backward_begin")
     _lib.check(lib.sclip_backward_tiles(byref(pb), ws.ptr, _ptr(t3), _ptr(g3), st), "sclip_backward_tiles")
+    _mark("backward_tiles")
     _lib.check(lib.sclip_backward_gemms(byref(pb), ws.ptr, _ptr(t3), _ptr(g3), st), "sclip_backward_gemms")
+    _mark("backward_gemms")
     col = None
     mult = 1.0
     if pb.world > 1:
@@ -215,12 +233,14 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
         col = torch.empty((3, bl, d), dtype=torch.float32, device=img.device)
         for m in range(3):  # reduce-scatter of the column-role partial gradients
             dist.reduce_scatter_tensor(col[m], part[m], group=cfg.process_group)
+        _mark("reduce_scatter")
         if cfg.grad_scale == "ddp":
             mult = float(pb.world)
     _lib.check(
         lib.sclip_backward_finish(byref(pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3), _ptr(g3), _ptr(col),
                                   ctypes.c_float(mult), _ptr(dimg), _ptr(dtxt), _ptr(daud), out_f32, _ptr(dt3), st),
         "sclip_backward_finish")
+    _mark("backward_finish")
     if pb.world > 1 and cfg.grad_scale == "sum":
         import torch.distributed as dist
 

@@ -78,6 +78,9 @@ typedef struct sclip_layout {
   uint64_t lse_row;       /* [3][rows_local] fp32                                                            */
   uint64_t lse_col_local; /* [3][rows_global] fp32 column log-sum-exp over this rank's rows [exchange: all-gather] */
   uint64_t lse_col;       /* [3][rows_global] fp32 column log-sum-exp over all rows                          */
+  uint64_t row_inv;       /* [3][rows_local] fp32 1 / sum_j exp(L_ij)   (only used while exp(logit_scale) < 64)   */
+  uint64_t col_sum_local; /* [3][rows_global] fp32 sum over this rank's rows of exp(L_ij) (same condition)        */
+  uint64_t col_inv;       /* [3][rows_global] fp32 1 / sum_i exp(L_ij) over all rows (same condition)             */
   uint64_t loss_part;     /* [3] fp32 this rank's share of the three losses [exchange: all-reduce sum]       */
   uint64_t grad_tiles;    /* [3][rows_local][ld_g] fp16 scaled softmax-gradient strip G'                     */
   uint64_t grad_tiles_lo; /* low halves (SCLIP_MATH_F16X3 only)                                              */

@@ -25,7 +25,10 @@ constexpr int kTileThreads = 192;            // warp 0: TMA, warp 1: MMA + TMEM 
 constexpr int kTileSmemBytes = kStages * STAGE_BYTES + 1024;  // + slack for the 1024-byte alignment
 
 constexpr float kKappa = 32768.0f;           // scale of the fp16 softmax-gradient tiles (|G'| <= kappa)
-constexpr float kFastPathMaxScale = 40.0f;   // exp(-2 s) must stay a normal fp32 number for the fixed reference
+// While s = exp(logit_scale) < 64 every exp(+-s) and every row / column sum of exp(logit) is a normal fp32 number
+// (|logit| <= s because the operands are cosines), so the exponentials need no reference shift at all.  Above that
+// (e.g. CLIP's clamp at s = 100) each tile is shifted by its own maximum and the backward uses log-sum-exps.
+constexpr float kFastPathMaxScale = 64.0f;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kOperandScaleX3 = 256.0f;    // xhat is stored as 256*xhat in the F16X3 mode (keeps lo parts normal)
 
@@ -47,6 +50,7 @@ struct Segment {
 struct Job {
   Segment seg[kMaxSegments];
   int nseg;
+  int ksplits;   // >1: the k blocks of every segment are divided over this many CTAs which add into the output
   int m_tiles;   // BM tiles
   int n_tiles;   // BN tiles
   int tile_base; // first linear tile id of this job inside a batched launch
@@ -86,6 +90,9 @@ struct Workspace {  // resolved device pointers of one workspace blob
   float* lse_row;
   float* lse_col_local;
   float* lse_col;
+  float* row_inv;
+  float* col_sum_local;
+  float* col_inv;
   float* loss_part;
   __half* g[3];
   __half* g_lo[3];
@@ -117,6 +124,8 @@ struct BwdParams {
   const float* g3;
   const float* lse_row;
   const float* lse_col;
+  const float* row_inv;
+  const float* col_inv;
   float* dt_part;
   int rows_local, rows_global, row_offset;
   int nti, ntj;

@@ -82,6 +82,9 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->lse_row = take(3 * bl * 4);
   lay->lse_col_local = take(3 * bg * 4);
   lay->lse_col = take(3 * bg * 4);
+  lay->row_inv = take(3 * bl * 4);
+  lay->col_sum_local = take(3 * bg * 4);
+  lay->col_inv = take(3 * bg * 4);
   lay->loss_part = take(3 * 4);
   lay->grad_tiles = take(3 * bl * ldg * 2);
   lay->grad_tiles_lo = x3 ? take(3 * bl * ldg * 2) : lay->grad_tiles;
@@ -119,6 +122,9 @@ int resolve(const sclip_problem* pb, void* ws, Workspace* w) {
   w->lse_row = reinterpret_cast<float*>(b + l.lse_row);
   w->lse_col_local = reinterpret_cast<float*>(b + l.lse_col_local);
   w->lse_col = reinterpret_cast<float*>(b + l.lse_col);
+  w->row_inv = reinterpret_cast<float*>(b + l.row_inv);
+  w->col_sum_local = reinterpret_cast<float*>(b + l.col_sum_local);
+  w->col_inv = reinterpret_cast<float*>(b + l.col_inv);
   w->loss_part = reinterpret_cast<float*>(b + l.loss_part);
   w->dt_part = reinterpret_cast<float*>(b + l.dt_part);
   w->dxhat_row = reinterpret_cast<float*>(b + l.dxhat_row);
@@ -244,13 +250,14 @@ void similarity_job(const Workspace& w, MapTable& t, int p, Job* job) {
   const int rm = pair_row_modality(p), cm = pair_col_modality(p);
   const int nkb = ceil_div(w.pb.dim, BK);
   memset(job, 0, sizeof(*job));
-  job->seg[0] = seg(t.use(kXhatRowsK + rm), t.use(kXhatColsK + cm), 0, 0, nkb);
-  job->nseg = 1;
+  // F16X3: the two small cross products go first so that the tensor core's truncating fp32 accumulation works on
+  // small partial sums for two thirds of the k range
   if (w.pb.math == SCLIP_MATH_F16X3) {
-    job->seg[1] = seg(t.use(kXloRowsK + rm), t.use(kXhatColsK + cm), 0, 0, nkb);
-    job->seg[2] = seg(t.use(kXhatRowsK + rm), t.use(kXloColsK + cm), 0, 0, nkb);
-    job->nseg = 3;
+    job->seg[job->nseg++] = seg(t.use(kXloRowsK + rm), t.use(kXhatColsK + cm), 0, 0, nkb);
+    job->seg[job->nseg++] = seg(t.use(kXhatRowsK + rm), t.use(kXloColsK + cm), 0, 0, nkb);
   }
+  job->seg[job->nseg++] = seg(t.use(kXhatRowsK + rm), t.use(kXhatColsK + cm), 0, 0, nkb);
+  job->ksplits = 1;
   job->m_tiles = w.lay.row_tiles;
   job->n_tiles = w.lay.col_tiles;
 }
@@ -346,6 +353,8 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
   p.g3 = g3;
   p.lse_row = w.lse_row;
   p.lse_col = w.lse_col;
+  p.row_inv = w.row_inv;
+  p.col_inv = w.col_inv;
   p.dt_part = w.dt_part;
   p.rows_local = w.pb.rows_local;
   p.rows_global = w.pb.rows_global;
@@ -375,22 +384,30 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
   p.g3 = g3;
   // dXhat = (max_q |s_q g_q| / (kappa B)) G' Xhat ; operands of the F16X3 mode carry an extra factor 256
   p.alpha0 = 1.0f / (kKappa * static_cast<float>(pb.rows_global)) / (x3 ? kOperandScaleX3 : 1.0f);
+  // F16X3 (fp32 parity mode): bound the length of one tensor-core accumulation chain to 1024 k elements; the
+  // chunks are combined with round-to-nearest fp32 adds (red.global.add.f32 into the zeroed output)
+  auto splits_for = [&](int kb) { return x3 ? ceil_div(kb, 16) : 1; };
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x3) {
+    SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_row, 0, 3 * bl * d * 4, st));
+    if (pb.world > 1) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
+  }
   int nj = 0, tiles = 0;
   auto add_role = [&](Job& job, int m, bool row_role) {
     if (row_role) {  // G'_{pair m} (rows_local x rows_global, K-major) . xhat_{col modality} (k = global row)
       const int pr = modality_row_pair(m), cm = pair_col_modality(pr);
-      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
       if (x3) {
         job.seg[job.nseg++] = seg(tab.use(kGloK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
         job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
       }
+      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
     } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
       const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
-      job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
       if (x3) {
         job.seg[job.nseg++] = seg(tab.use(kGloMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
         job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXloLocMN + rm), 1, 1, kb_l);
       }
+      job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
     }
   };
   for (int m = 0; m < 3; ++m) {
@@ -399,8 +416,9 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
     if (pb.world == 1) add_role(job, m, false);
     job.m_tiles = ceil_div(pb.rows_local, BM);
     job.n_tiles = ceil_div(pb.dim, BN);
+    job.ksplits = splits_for(pb.world == 1 ? (kb_g > kb_l ? kb_g : kb_l) : kb_g);
     job.tile_base = tiles;
-    tiles += job.m_tiles * job.n_tiles;
+    tiles += job.m_tiles * job.n_tiles * job.ksplits;
     p.out[nj] = w.dxhat_row + m * bl * d;
     p.ldc[nj] = pb.dim;
     p.m[nj] = pb.rows_local;
@@ -413,8 +431,9 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
       add_role(job, m, false);
       job.m_tiles = ceil_div(pb.rows_global, BM);
       job.n_tiles = ceil_div(pb.dim, BN);
+      job.ksplits = splits_for(kb_l);
       job.tile_base = tiles;
-      tiles += job.m_tiles * job.n_tiles;
+      tiles += job.m_tiles * job.n_tiles * job.ksplits;
       p.out[nj] = w.dxhat_col + m * bg * d;
       p.ldc[nj] = pb.dim;
       p.m[nj] = pb.rows_global;
@@ -425,7 +444,7 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
   if (tab.rc) return tab.rc;
   p.njobs = nj;
   p.total_tiles = tiles;
-  return launch_gemm(p, static_cast<cudaStream_t>(stream));
+  return launch_gemm(p, st);
 }
 
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
@@ -492,6 +511,7 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK)};
   p.jobs[0].nseg = 1;
+  p.jobs[0].ksplits = 1;
   p.jobs[0].m_tiles = ceil_div(m, BM);
   p.jobs[0].n_tiles = ceil_div(n, BN);
   p.jobs[0].tile_base = 0;

@@ -117,6 +117,8 @@ struct ReduceArgs {
   const float* tile_ref;
   float* lse_row;
   float* lse_col_local;
+  float* row_inv;
+  float* col_sum_local;
   int* status;
   int rows_local, rows_global, nti, ntj;
 };
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a)
       sum += a.row_part[(static_cast<size_t>(p) * a.ntj + tj) * a.rows_local + i] * __expf(ref[tj] - R);
     const float lse = R + logf(sum);
     a.lse_row[static_cast<size_t>(p) * a.rows_local + i] = lse;
+    a.row_inv[static_cast<size_t>(p) * a.rows_local + i] = 1.0f / sum;  // meaningful when every tile reference is 0
     bad |= !isfinite(lse);
   }
   if (i < a.rows_global) {
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a)
              __expf(a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj] - R);
     const float lse = R + logf(sum);
     a.lse_col_local[static_cast<size_t>(p) * a.rows_global + i] = lse;
+    a.col_sum_local[static_cast<size_t>(p) * a.rows_global + i] = sum;
     bad |= !isfinite(lse);
   }
   if (bad) atomicOr(a.status, 1);
@@ -158,7 +162,9 @@ struct LossArgs {
   const float* lse_col_local;
   const float* col_lse_all;  // [world][3][rows_global] or null
   const float* diag;
+  const float* col_sum_local;
   float* lse_col;
+  float* col_inv;
   float* loss_part;
   float* loss3;
   int rows_local, rows_global, row_offset, world;
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(1024) forward_loss_kernel(const LossArgs a) {
     float v;
     if (a.col_lse_all == nullptr) {
       v = a.lse_col_local[static_cast<size_t>(p) * a.rows_global + j];
+      a.col_inv[static_cast<size_t>(p) * a.rows_global + j] = 1.0f / a.col_sum_local[static_cast<size_t>(p) * a.rows_global + j];
     } else {
       float mx = -INFINITY;
       for (int w = 0; w < a.world; ++w)
@@ -180,6 +187,7 @@ __global__ void __launch_bounds__(1024) forward_loss_kernel(const LossArgs a) {
       for (int w = 0; w < a.world; ++w)
         sum += expf(a.col_lse_all[(static_cast<size_t>(w) * 3 + p) * a.rows_global + j] - mx);
       v = mx + logf(sum);
+      a.col_inv[static_cast<size_t>(p) * a.rows_global + j] = expf(-v);
     }
     lse_col[j] = v;
   }
@@ -314,7 +322,7 @@ int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t st
 }
 
 int launch_forward_reduce(const Workspace& w, cudaStream_t stream) {
-  ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.lse_row, w.lse_col_local, w.status,
+  ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.lse_row, w.lse_col_local, w.row_inv, w.col_sum_local, w.status,
                w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, w.lay.col_tiles};
   const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
   dim3 grid((n + 255) / 256, 3);
@@ -324,7 +332,7 @@ int launch_forward_reduce(const Workspace& w, cudaStream_t stream) {
 }
 
 int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream) {
-  LossArgs a{w.lse_row, w.lse_col_local, col_lse_all, w.diag, w.lse_col, w.loss_part, loss3,
+  LossArgs a{w.lse_row, w.lse_col_local, col_lse_all, w.diag, w.col_sum_local, w.lse_col, w.col_inv, w.loss_part, loss3,
              w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, w.pb.world};
   forward_loss_kernel<<<3, 1024, 0, stream>>>(a);
   SCLIP_CUDA_OK(cudaGetLastError());

@@ -33,15 +33,23 @@ __device__ __forceinline__ uint8_t* aligned_dyn_smem() {
 }
 
 // ---------------------------------------------------------------------------------------------- mainloop roles
+// k blocks [lo, hi) of a segment handled by split `split` of `ksplits`
+__device__ __forceinline__ void split_range(int num_kb, int split, int ksplits, int& lo, int& hi) {
+  lo = static_cast<int>((static_cast<long long>(num_kb) * split) / ksplits);
+  hi = static_cast<int>((static_cast<long long>(num_kb) * (split + 1)) / ksplits);
+}
+
 __device__ __forceinline__ void producer_loop(const CUtensorMap* maps, const Job& job, int m0, int n0, uint8_t* smem,
-                                              PipeBarriers* bars) {
+                                              PipeBarriers* bars, int split = 0, int ksplits = 1) {
   int stage = 0;
   uint32_t phase = 0;
   for (int s = 0; s < job.nseg; ++s) {
     const Segment seg = job.seg[s];
     const CUtensorMap* ma = maps + seg.map_a;
     const CUtensorMap* mb = maps + seg.map_b;
-    for (int kb = 0; kb < seg.num_kb; ++kb) {
+    int kb_lo, kb_hi;
+    split_range(seg.num_kb, split, ksplits, kb_lo, kb_hi);
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
       mbar_wait_bounded(&bars->empty[stage], phase ^ 1u, 1);
       mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
       uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -67,14 +75,17 @@ __device__ __forceinline__ void producer_loop(const CUtensorMap* maps, const Job
   }
 }
 
-__device__ __forceinline__ void mma_loop(const Job& job, uint8_t* smem, PipeBarriers* bars, uint32_t tmem_acc) {
+__device__ __forceinline__ void mma_loop(const Job& job, uint8_t* smem, PipeBarriers* bars, uint32_t tmem_acc,
+                                         int split = 0, int ksplits = 1) {
   int stage = 0;
   uint32_t phase = 0;
   uint32_t accumulate = 0;
   for (int s = 0; s < job.nseg; ++s) {
     const Segment seg = job.seg[s];
     const uint32_t idesc = make_idesc_f16(BM, BN, /*fp16*/ 0, seg.a_mn, seg.b_mn);
-    for (int kb = 0; kb < seg.num_kb; ++kb) {
+    int kb_lo, kb_hi;
+    split_range(seg.num_kb, split, ksplits, kb_lo, kb_hi);
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
       mbar_wait_bounded(&bars->full[stage], phase, 2);
       tc_fence_after();
       const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
@@ -209,9 +220,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) forward_tiles_kernel(const __
     mbar_wait_bounded(&bars.tmem_full, 0, 3);
     tc_fence_after();
 
-    // exponent reference of this tile, in log2 units.  s < 40: the bound |logit| <= s (cosines) is used as a fixed
-    // reference; otherwise the true maximum of the tile is taken in a first pass over TMEM.
-    float ref2 = s * kLog2e;
+    // exponent reference of this tile, in log2 units.  s < 64: |logit| <= s (cosines), so exp(logit) and its sums are
+    // normal fp32 numbers without any shift; otherwise the true maximum of the tile is taken in a first pass over TMEM.
+    float ref2 = 0.f;
     if (!(s < kFastPathMaxScale)) {
       float mx = -INFINITY;
       for (int ch = 0; ch < BN / 32; ++ch) {
@@ -317,13 +328,16 @@ __global__ void __launch_bounds__(kTileThreads, 2) backward_tiles_kernel(const _
     const bool has_lo = P.store_map_lo[p] >= 0;
 
     // per-row / per-column softmax normalisers, prepared while the MMAs run
-    const float lse_r = row_ok ? P.lse_row[static_cast<size_t>(p) * P.rows_local + row] : 0.f;
-    const float rowfac = fast ? expf(s - lse_r) : lse_r * kLog2e;
+    // fast path: reciprocal row / column sums of exp(logit); safe path: log-sum-exps in log2 units
+    const float* rown = fast ? P.row_inv : P.lse_row;
+    const float* coln = fast ? P.col_inv : P.lse_col;
+    const float rown_v = row_ok ? rown[static_cast<size_t>(p) * P.rows_local + row] : 0.f;
+    const float rowfac = fast ? rown_v : rown_v * kLog2e;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int cc = epi_tid + h * 128;
-      const float lse_c = (n0 + cc < P.rows_global) ? P.lse_col[static_cast<size_t>(p) * P.rows_global + n0 + cc] : 0.f;
-      colfac[cc] = fast ? expf(s - lse_c) : lse_c * kLog2e;
+      const float coln_v = (n0 + cc < P.rows_global) ? coln[static_cast<size_t>(p) * P.rows_global + n0 + cc] : 0.f;
+      colfac[cc] = fast ? coln_v : coln_v * kLog2e;
     }
     named_bar_sync(kEpiBarrier, kEpiThreads);
 
@@ -331,7 +345,6 @@ __global__ void __launch_bounds__(kTileThreads, 2) backward_tiles_kernel(const _
     tc_fence_after();
     // all TMA loads have landed and every MMA has completed: the pipeline stages are free to stage the G' tiles.
     // layout: hi slabs at [0, 32 KiB) (two 16 KiB buffers), lo slabs at [32 KiB, 64 KiB)
-    const float ref2 = s * kLog2e;
     float dtacc = 0.f;
     const CUtensorMap* map_hi = &P.maps[P.store_map[p]];
     const CUtensorMap* map_lo = has_lo ? &P.maps[P.store_map_lo[p]] : nullptr;
@@ -356,7 +369,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) backward_tiles_kernel(const _
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             const float a = __uint_as_float(v[k]);
-            const float e = ex2_approx(fmaf(a, c, -ref2));
+            const float e = ex2_approx(a * c);
             g[k] = (e * (rowfac + colfac[ch * 32 + k])) * half_kc;
           }
         } else {
@@ -430,19 +443,22 @@ __global__ void __launch_bounds__(kTileThreads, 2) gemm_tiles_kernel(const __gri
   const Job& job = P.jobs[j];
   const int local = blockIdx.x - job.tile_base;
   const int tn = local % job.n_tiles;  // n fastest: the CTAs sharing an A row panel run together
-  const int tm = local / job.n_tiles;
+  const int rest = local / job.n_tiles;
+  const int split = rest % job.ksplits;
+  const int tm = rest / job.ksplits;
   const int m0 = tm * BM, n0 = tn * BN;
 
   const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
 
   if (warp == 0) {
-    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars);
+    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars, split, job.ksplits);
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc);
+    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc, split, job.ksplits);
     __syncwarp();
   } else {
     const int q = warp & 3;
+    const bool accumulate_out = job.ksplits > 1;
     float alpha = P.alpha0;
     if (P.t3 != nullptr) {
       float mx = 0.f;
@@ -471,7 +487,15 @@ __global__ void __launch_bounds__(kTileThreads, 2) gemm_tiles_kernel(const __gri
             o.y = __uint_as_float(v[k4 * 4 + 1]) * alpha;
             o.z = __uint_as_float(v[k4 * 4 + 2]) * alpha;
             o.w = __uint_as_float(v[k4 * 4 + 3]) * alpha;
-            *reinterpret_cast<float4*>(out + ch * 32 + k4 * 4) = o;
+            float* dst = out + ch * 32 + k4 * 4;
+            if (!accumulate_out) {
+              *reinterpret_cast<float4*>(dst) = o;
+            } else {  // k-split chunks are combined with round-to-nearest fp32 adds in L2
+              red_add_f32(dst + 0, o.x);
+              red_add_f32(dst + 1, o.y);
+              red_add_f32(dst + 2, o.z);
+              red_add_f32(dst + 3, o.w);
+            }
           }
         }
       }

@@ -67,10 +67,11 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
 
-        _build.build()
+    # incremental: a no-op when the digest of the sources matches the built library; raises when the library is
+    # missing or stale and nvcc is not available (there is no other implementation to fall back to)
+    _build.build()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in _PROTOTYPES.items():
         fn = getattr(lib, name)

@@ -40,7 +40,10 @@ def golden_errors(meta, data, res):
     """Relative errors of ``res`` against the golden payload (Frobenius-relative for gradients)."""
     errs = {
         "loss": float(np.max(np.abs(res["loss"] - data["loss"]) / np.abs(data["loss"]))),
-        "dscale": float(np.max(np.abs(res["dscale"] - data["dscale"]) / np.abs(data["dscale"]))),
+        # the three dlogit_scale values are compared like a gradient tensor (relative to its largest entry): a
+        # component can be close to zero by cancellation (expected logit vs diagonal logit), where even the
+        # reference's own fp32 run is only 1.3e-5 from its fp64 run (b2048x512_planted, third pair)
+        "dscale": float(np.max(np.abs(res["dscale"] - data["dscale"])) / np.max(np.abs(data["dscale"]))),
     }
     rng = np.random.default_rng(meta["seed"] + 7919)
     rows = np.sort(rng.choice(meta["B"], size=min(16, meta["B"]), replace=False))

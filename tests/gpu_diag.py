@@ -70,7 +70,7 @@ def run_case(b, d, dtype, t3, g3, seed, planted, math_mode, tol_loss, tol_grad, 
     loss3, dimg, dtxt, daud, dt3 = ops.forward_backward_raw(*ten, t3d, g3d, cfg)
     torch.cuda.synchronize()
     report(f"{label} loss", float(np.max(np.abs(loss3.cpu().numpy() - want["loss"]) / np.abs(want["loss"]))), tol_loss)
-    report(f"{label} dscale", float(np.max(np.abs(dt3.cpu().numpy() - want["dscale"]) / np.abs(want["dscale"]))), tol_grad)
+    report(f"{label} dscale", float(np.max(np.abs(dt3.cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"]))), tol_grad)
     for nm, g in (("dimg", dimg), ("dtxt", dtxt), ("daud", daud)):
         report(f"{label} {nm}", rel(g.float().cpu().numpy(), want[nm]), tol_grad)
 

@@ -20,9 +20,6 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int MN_BOX_BYTES = 64 * BK * 2;    // one 64(mn) x 64(k) box of an MN-major operand
-constexpr int kStages = 2;                   // per CTA; two CTAs are co-resident per SM
-constexpr int kTileThreads = 192;            // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-5: epilogue
-constexpr int kTileSmemBytes = kStages * STAGE_BYTES + 1024;  // + slack for the 1024-byte alignment
 
 constexpr float kKappa = 32768.0f;           // scale of the fp16 softmax-gradient tiles (|G'| <= kappa)
 // While s = exp(logit_scale) < 64 every exp(+-s) and every row / column sum of exp(logit) is a normal fp32 number
@@ -111,7 +108,8 @@ struct FwdParams {
   float* tile_ref;
   float* diag;
   int rows_local, rows_global, row_offset;
-  int nti, ntj;
+  int nti, ntj;     // layout strides: 128-row tiles (padded to even) and 256-column tiles
+  int stages;       // depth of the TMA ring
   float acc_scale;  // accumulator -> cosine (1 in F16 mode, 2^-16 in F16X3 mode)
 };
 
@@ -129,6 +127,7 @@ struct BwdParams {
   float* dt_part;
   int rows_local, rows_global, row_offset;
   int nti, ntj;
+  int stages;
   float acc_scale;
 };
 
@@ -141,17 +140,23 @@ struct GemmParams {
   int n[kMaxJobs];
   int njobs;
   int total_tiles;
+  int stages;
   const float* t3;   // when non-null alpha = alpha0 * max_q |exp(t_q) g_q| (backward); else alpha = alpha0
   const float* g3;
   float alpha0;
 };
 
-int launch_forward_tiles(const FwdParams& p, cudaStream_t stream);
-int launch_backward_tiles(const BwdParams& p, cudaStream_t stream);
-int launch_gemm(const GemmParams& p, cudaStream_t stream);
+// cg = 1: one CTA per tile of 128 rows; cg = 2: CTA pairs (cta_group::2) on tiles of 256 rows
+// ew = 8 | 16 epilogue warps per CTA
+int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream);
+int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t stream);
+int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream);
+int cta_group();   // SCLIP_CTA_GROUP environment override (1 or 2), default 2
+int epi_warps();   // SCLIP_EPI_WARPS environment override (8 or 16), default 16
+int staging_slabs(int ew, bool split);  // 16 KiB G' staging slabs the backward tile kernel needs
 
 int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream);
-int launch_forward_reduce(const Workspace& w, cudaStream_t stream);
+int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream);
 int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream);
 int launch_backward_finish(const Workspace& w, const void* const x3[3], const float* t3, const float* g3,
                            const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, float* dt3,

@@ -61,7 +61,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // arrive on the barrier at the same offset in CTA `cta_rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) {
   uint32_t remote = mapa(smem_u32(bar), cta_rank);
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -202,6 +202,24 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+// TMEM -> registers, 16 lanes x 256 bit, 4 repetitions along the columns (16 lanes x 32 fp32 columns, 16 registers):
+//   v[o + 4 n + 2 h + c] = lane (base + 8 h + t / 4), column (8 n + 2 (t % 4) + c)        t = thread in the warp
+// (the mma-style fragment: every thread holds 2 x 2 elements of each 16 x 8 sub-block)
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// A 32-lane x 32-column block of the warp's lane quarter as two of the above:
+//   v[16 g + 4 n + 2 h + c] = lane (16 g + 8 h + t / 4), column (8 n + 2 (t % 4) + c)
+__device__ __forceinline__ void tmem_ld_block32(uint32_t taddr, uint32_t (&v)[32]) {
+  tmem_ld_16x256b_x4(taddr, &v[0]);
+  tmem_ld_16x256b_x4(taddr + (16u << 16), &v[16]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -1,6 +1,7 @@
 // C ABI of the sclip library (include/sclip.h): argument checking, workspace layout, TMA descriptor
 // construction and the stage launchers.  Host code only; the kernels live in sclip_tc.cu / sclip_simt.cu.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <cudaTypedefs.h>
 
@@ -17,7 +18,33 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int cta_group() {
+  static int cached = 0;
+  if (cached == 0) {
+    const char* e = getenv("SCLIP_CTA_GROUP");
+    cached = (e != nullptr && e[0] == '1') ? 1 : 2;
+  }
+  return cached;
+}
+
+int epi_warps() {
+  static int cached = 0;
+  if (cached == 0) {
+    const char* e = getenv("SCLIP_EPI_WARPS");
+    cached = (e != nullptr && e[0] == '8') ? 8 : 16;
+  }
+  return cached;
+}
+
 namespace {
+
+// deepest TMA ring that fits next to `slabs` 16 KiB staging slabs in the 227 KiB of one CTA
+int ring_stages(int slabs) {
+  const int stage_bytes = cta_group() == 2 ? (A_STAGE_BYTES + B_STAGE_BYTES / 2) : STAGE_BYTES;
+  const int budget = 227 * 1024 - 14 * 1024 - 1024 - slabs * 16384;  // static smem + alignment slack
+  int st = budget / stage_bytes;
+  return st > 6 ? 6 : (st < 2 ? 2 : st);
+}
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -62,7 +89,7 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   memset(lay, 0, sizeof(*lay));
   const uint64_t bl = pb->rows_local, bg = pb->rows_global, d = pb->dim;
   const bool x3 = pb->math == SCLIP_MATH_F16X3;
-  lay->row_tiles = ceil_div(pb->rows_local, BM);
+  lay->row_tiles = 2 * ceil_div(pb->rows_local, 2 * BM);  // even: a CTA pair works on 256 rows
   lay->col_tiles = ceil_div(pb->rows_global, BN);
   lay->ld_g = static_cast<int32_t>(align_up(bg, 64));
   const uint64_t nti = lay->row_tiles, ntj = lay->col_tiles, ldg = lay->ld_g;
@@ -202,9 +229,9 @@ int encode_slot(const Workspace& w, int slot, CUtensorMap* out) {
   const __half* loc_lo = w.xhat_lo[m] + static_cast<size_t>(pb.row_offset) * d;
   switch (slot - m) {
     case kXhatRowsK: return make_map(out, loc, d, bl, d, BK, BM);
-    case kXhatColsK: return make_map(out, w.xhat[m], d, bg, d, BK, BN);
+    case kXhatColsK: return make_map(out, w.xhat[m], d, bg, d, BK, BN / cta_group());
     case kXloRowsK: return make_map(out, loc_lo, d, bl, d, BK, BM);
-    case kXloColsK: return make_map(out, w.xhat_lo[m], d, bg, d, BK, BN);
+    case kXloColsK: return make_map(out, w.xhat_lo[m], d, bg, d, BK, BN / cta_group());
     case kGK: return make_map(out, w.g[m], bg, bl, ldg, 64, BM);
     case kGloK: return make_map(out, w.g_lo[m], bg, bl, ldg, 64, BM);
     case kGMN: return make_map(out, w.g[m], bg, bl, ldg, 64, BK);
@@ -313,15 +340,16 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
   p.row_offset = w.pb.row_offset;
   p.nti = w.lay.row_tiles;
   p.ntj = w.lay.col_tiles;
+  p.stages = ring_stages(0);
   p.acc_scale = w.pb.math == SCLIP_MATH_F16X3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
-  return launch_forward_tiles(p, static_cast<cudaStream_t>(stream));
+  return launch_forward_tiles(p, cta_group(), epi_warps(), static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
-  return launch_forward_reduce(w, static_cast<cudaStream_t>(stream));
+  return launch_forward_reduce(w, w.lay.row_tiles, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_lse_all, float* loss3, void* stream) {
@@ -361,8 +389,9 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
   p.row_offset = w.pb.row_offset;
   p.nti = w.lay.row_tiles;
   p.ntj = w.lay.col_tiles;
+  p.stages = ring_stages(staging_slabs(epi_warps(), x3));
   p.acc_scale = x3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
-  return launch_backward_tiles(p, static_cast<cudaStream_t>(stream));
+  return launch_backward_tiles(p, cta_group(), epi_warps(), static_cast<cudaStream_t>(stream));
 }
 
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
@@ -414,7 +443,7 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
     Job& job = p.jobs[nj];
     add_role(job, m, true);
     if (pb.world == 1) add_role(job, m, false);
-    job.m_tiles = ceil_div(pb.rows_local, BM);
+    job.m_tiles = ceil_div(pb.rows_local, BM * cta_group());
     job.n_tiles = ceil_div(pb.dim, BN);
     job.ksplits = splits_for(pb.world == 1 ? (kb_g > kb_l ? kb_g : kb_l) : kb_g);
     job.tile_base = tiles;
@@ -429,7 +458,7 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
     for (int m = 0; m < 3; ++m) {
       Job& job = p.jobs[nj];
       add_role(job, m, false);
-      job.m_tiles = ceil_div(pb.rows_global, BM);
+      job.m_tiles = ceil_div(pb.rows_global, BM * cta_group());
       job.n_tiles = ceil_div(pb.dim, BN);
       job.ksplits = splits_for(kb_l);
       job.tile_base = tiles;
@@ -444,7 +473,8 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
   if (tab.rc) return tab.rc;
   p.njobs = nj;
   p.total_tiles = tiles;
-  return launch_gemm(p, st);
+  p.stages = ring_stages(0);
+  return launch_gemm(p, cta_group(), epi_warps(), st);
 }
 
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
@@ -506,13 +536,14 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc = a_mn ? make_map(&p.maps[0], a, m, k, lda, 64, BK) : make_map(&p.maps[0], a, k, m, lda, BK, BM);
-  if (!rc) rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN);
+  if (!rc)
+    rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN / cta_group());
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK)};
   p.jobs[0].nseg = 1;
   p.jobs[0].ksplits = 1;
-  p.jobs[0].m_tiles = ceil_div(m, BM);
+  p.jobs[0].m_tiles = ceil_div(m, BM * cta_group());
   p.jobs[0].n_tiles = ceil_div(n, BN);
   p.jobs[0].tile_base = 0;
   p.out[0] = c;
@@ -522,7 +553,8 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
   p.njobs = 1;
   p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles;
   p.alpha0 = alpha;
-  return launch_gemm(p, st);
+  p.stages = ring_stages(0);
+  return launch_gemm(p, cta_group(), epi_warps(), st);
 }
 
 }  // extern "C"

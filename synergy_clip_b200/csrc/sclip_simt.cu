@@ -120,7 +120,10 @@ struct ReduceArgs {
   float* row_inv;
   float* col_sum_local;
   int* status;
-  int rows_local, rows_global, nti, ntj;
+  int rows_local, rows_global;
+  int nti;       // layout stride (128-row tiles, padded)
+  int nti_done;  // 128-row tiles the forward kernel actually produced
+  int ntj;
 };
 
 __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a) {
@@ -143,9 +146,9 @@ __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a)
   if (i < a.rows_global) {
     const int tj = i / BN;
     float R = -INFINITY;
-    for (int ti = 0; ti < a.nti; ++ti) R = fmaxf(R, a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj]);
+    for (int ti = 0; ti < a.nti_done; ++ti) R = fmaxf(R, a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj]);
     float sum = 0.f;
-    for (int ti = 0; ti < a.nti; ++ti)
+    for (int ti = 0; ti < a.nti_done; ++ti)
       sum += a.col_part[(static_cast<size_t>(p) * a.nti + ti) * a.rows_global + i] *
              __expf(a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj] - R);
     const float lse = R + logf(sum);
@@ -321,9 +324,9 @@ int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t st
   return SCLIP_OK;
 }
 
-int launch_forward_reduce(const Workspace& w, cudaStream_t stream) {
+int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream) {
   ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.lse_row, w.lse_col_local, w.row_inv, w.col_sum_local, w.status,
-               w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, w.lay.col_tiles};
+               w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, row_tiles_done, w.lay.col_tiles};
   const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
   dim3 grid((n + 255) / 256, 3);
   forward_reduce_kernel<<<grid, 256, 0, stream>>>(a);

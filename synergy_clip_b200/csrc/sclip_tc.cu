@@ -6,9 +6,13 @@
 //                   + partial sums of dL/dlogit_scale                               (autograd of model.py:52-58)
 //   gemm            dXhat = G' . Xhat_cols,  dXhat += G'^T . Xhat_rows              (autograd of model.py:255,260,265)
 //
-// All three share one mainloop: warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer and TMEM owner,
-// warps 2-5 = epilogue (one TMEM lane quarter each).  One 128x256 fp32 accumulator (256 TMEM columns) per CTA,
-// two CTAs per SM so one CTA's epilogue overlaps the other's MMAs.
+// One persistent CTA per SM (or one CTA pair per two SMs with cta_group::2), looping over tiles:
+//   warp 0      TMA producer: ring of `stages` k blocks (A: 128 x 64, B: 256/CG x 64 fp16, 128-byte swizzle)
+//   warp 1      single-thread tcgen05.mma issuer (leader CTA only when CG == 2) and TMEM owner
+//   warps 2..   epilogue: EW = 8 or 16 warps, EW / 4 per TMEM lane quarter, each on its slice of the 256 columns
+// The 512 TMEM columns hold two 128x256 fp32 accumulators, so the epilogue of tile n runs under the MMAs of tile n+1.
+#include <cstring>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -17,12 +21,24 @@ using namespace ptx;
 
 namespace {
 
+constexpr int kMaxStages = 6;
+constexpr int kAccStages = 2;
+constexpr int kMaxEpiWarps = 16;
+
 struct __align__(8) PipeBarriers {
-  uint64_t full[kStages];
-  uint64_t empty[kStages];
-  uint64_t tmem_full;
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[kAccStages];
+  uint64_t tmem_empty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad;
+};
+
+template <int CG>
+struct Geo {
+  static constexpr int kBRows = BN / CG;                               // B rows loaded by one CTA per stage
+  static constexpr int kStageBytes = A_STAGE_BYTES + kBRows * BK * 2;  // 48 KiB (CG 1) / 32 KiB (CG 2)
+  static constexpr int kTileM = BM * CG;                               // rows of one cluster tile
 };
 
 __device__ __forceinline__ uint8_t* aligned_dyn_smem() {
@@ -32,63 +48,104 @@ __device__ __forceinline__ uint8_t* aligned_dyn_smem() {
   return dyn_smem_raw + pad;
 }
 
-// ---------------------------------------------------------------------------------------------- mainloop roles
+struct Tile {
+  int job;    // job / pair index
+  int m0;     // first row of the cluster tile
+  int n0;     // first column
+  int split;  // k split index
+  int ti;     // cluster-row-tile index
+  int tj;
+};
+
+struct RingState {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int stages) {
+    if (++stage == stages) {
+      stage = 0;
+      phase ^= 1u;
+    }
+  }
+};
+
 // k blocks [lo, hi) of a segment handled by split `split` of `ksplits`
 __device__ __forceinline__ void split_range(int num_kb, int split, int ksplits, int& lo, int& hi) {
   lo = static_cast<int>((static_cast<long long>(num_kb) * split) / ksplits);
   hi = static_cast<int>((static_cast<long long>(num_kb) * (split + 1)) / ksplits);
 }
 
-__device__ __forceinline__ void producer_loop(const CUtensorMap* maps, const Job& job, int m0, int n0, uint8_t* smem,
-                                              PipeBarriers* bars, int split = 0, int ksplits = 1) {
-  int stage = 0;
-  uint32_t phase = 0;
+// ---------------------------------------------------------------------------------------------- mainloop roles
+template <int CG>
+__device__ __forceinline__ void producer_tile(const CUtensorMap* maps, const Job& job, const Tile& t, uint32_t rank,
+                                              uint8_t* smem, PipeBarriers* bars, int stages, RingState& rs) {
+  using G = Geo<CG>;
+  const int m0 = t.m0 + static_cast<int>(rank) * BM;         // this CTA's accumulator rows
+  const int n0 = t.n0 + static_cast<int>(rank) * G::kBRows;  // this CTA's share of the B rows
   for (int s = 0; s < job.nseg; ++s) {
     const Segment seg = job.seg[s];
     const CUtensorMap* ma = maps + seg.map_a;
     const CUtensorMap* mb = maps + seg.map_b;
     int kb_lo, kb_hi;
-    split_range(seg.num_kb, split, ksplits, kb_lo, kb_hi);
+    split_range(seg.num_kb, t.split, job.ksplits, kb_lo, kb_hi);
     for (int kb = kb_lo; kb < kb_hi; ++kb) {
-      mbar_wait_bounded(&bars->empty[stage], phase ^ 1u, 1);
-      mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
-      uint8_t* sa = smem + stage * STAGE_BYTES;
+      mbar_wait_bounded<false>(&bars->empty[rs.stage], rs.phase ^ 1u, 1);
+      uint8_t* sa = smem + rs.stage * G::kStageBytes;
       uint8_t* sb = sa + A_STAGE_BYTES;
       const int k = kb * BK;
-      if (!seg.a_mn) {
-        tma_load_2d(sa, ma, &bars->full[stage], k, m0);
-      } else {
+      if constexpr (CG == 1) {
+        uint64_t* bar = &bars->full[rs.stage];
+        mbar_expect_tx(bar, G::kStageBytes);
+        if (!seg.a_mn) {
+          tma_load_2d(sa, ma, bar, k, m0);
+        } else {
 #pragma unroll
-        for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * MN_BOX_BYTES, ma, &bars->full[stage], m0 + g * 64, k);
-      }
-      if (!seg.b_mn) {
-        tma_load_2d(sb, mb, &bars->full[stage], k, n0);
-      } else {
+          for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * MN_BOX_BYTES, ma, bar, m0 + g * 64, k);
+        }
+        if (!seg.b_mn) {
+          tma_load_2d(sb, mb, bar, k, n0);
+        } else {
 #pragma unroll
-        for (int g = 0; g < BN / 64; ++g) tma_load_2d(sb + g * MN_BOX_BYTES, mb, &bars->full[stage], n0 + g * 64, k);
+          for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
+        }
+      } else {
+        // both CTAs of the pair signal the leader's barrier; the leader arms it for the bytes of both
+        const uint32_t bar = mapa(smem_u32(&bars->full[rs.stage]), 0);
+        if (rank == 0) mbar_expect_tx(&bars->full[rs.stage], CG * G::kStageBytes);
+        if (!seg.a_mn) {
+          tma_load_2d_2sm(sa, ma, bar, k, m0);
+        } else {
+#pragma unroll
+          for (int g = 0; g < BM / 64; ++g) tma_load_2d_2sm(sa + g * MN_BOX_BYTES, ma, bar, m0 + g * 64, k);
+        }
+        if (!seg.b_mn) {
+          tma_load_2d_2sm(sb, mb, bar, k, n0);
+        } else {
+#pragma unroll
+          for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d_2sm(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
+        }
       }
-      if (++stage == kStages) {
-        stage = 0;
-        phase ^= 1u;
-      }
+      rs.advance(stages);
     }
   }
 }
 
-__device__ __forceinline__ void mma_loop(const Job& job, uint8_t* smem, PipeBarriers* bars, uint32_t tmem_acc,
-                                         int split = 0, int ksplits = 1) {
-  int stage = 0;
-  uint32_t phase = 0;
+template <int CG>
+__device__ __forceinline__ void mma_tile(const Job& job, const Tile& t, uint8_t* smem, PipeBarriers* bars, int stages,
+                                         RingState& rs, uint32_t tmem_acc, int acc, uint32_t acc_phase) {
+  using G = Geo<CG>;
+  // the epilogue must have drained this accumulator (two tiles ago)
+  mbar_wait_bounded<false>(&bars->tmem_empty[acc], acc_phase ^ 1u, 4);
+  tc_fence_after();
   uint32_t accumulate = 0;
   for (int s = 0; s < job.nseg; ++s) {
     const Segment seg = job.seg[s];
-    const uint32_t idesc = make_idesc_f16(BM, BN, /*fp16*/ 0, seg.a_mn, seg.b_mn);
+    const uint32_t idesc = make_idesc_f16(BM * CG, BN, /*fp16*/ 0, seg.a_mn, seg.b_mn);
     int kb_lo, kb_hi;
-    split_range(seg.num_kb, split, ksplits, kb_lo, kb_hi);
+    split_range(seg.num_kb, t.split, job.ksplits, kb_lo, kb_hi);
     for (int kb = kb_lo; kb < kb_hi; ++kb) {
-      mbar_wait_bounded(&bars->full[stage], phase, 2);
+      mbar_wait_bounded<false>(&bars->full[rs.stage], rs.phase, 2);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(smem + stage * STAGE_BYTES);
+      const uint32_t a_base = smem_u32(smem + rs.stage * G::kStageBytes);
       const uint32_t b_base = a_base + A_STAGE_BYTES;
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -98,53 +155,72 @@ __device__ __forceinline__ void mma_loop(const Job& job, uint8_t* smem, PipeBarr
                                         : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
         const uint64_t bdesc = seg.b_mn ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
                                         : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
-        umma_f16<1>(tmem_acc, adesc, bdesc, idesc, accumulate);
+        umma_f16<CG>(tmem_acc, adesc, bdesc, idesc, accumulate);
         accumulate = 1;
       }
-      umma_commit_1sm(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
-      if (++stage == kStages) {
-        stage = 0;
-        phase ^= 1u;
-      }
+      // frees the smem slot (in both CTAs) once these MMAs have read it
+      if constexpr (CG == 1) umma_commit_1sm(&bars->empty[rs.stage]);
+      else umma_commit_2sm(&bars->empty[rs.stage], 0b11);
+      rs.advance(stages);
     }
   }
-  umma_commit_1sm(&bars->tmem_full);  // accumulator complete
+  if constexpr (CG == 1) umma_commit_1sm(&bars->tmem_full[acc]);
+  else umma_commit_2sm(&bars->tmem_full[acc], 0b11);
 }
 
-// Common prologue: barrier init, TMEM allocation.  Returns the TMEM base address of the 256-column accumulator.
-__device__ __forceinline__ uint32_t tile_setup(PipeBarriers* bars, int warp, int lane) {
+// Common prologue: barrier init, TMEM allocation (all 512 columns = two accumulators).
+template <int CG, int EW>
+__device__ __forceinline__ uint32_t kernel_setup(PipeBarriers* bars, int warp, int lane) {
   if (warp == 0 && lane == 0) {
 #pragma unroll
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
     }
-    mbar_init(&bars->tmem_full, 1);
+#pragma unroll
+    for (int i = 0; i < kAccStages; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], CG * EW);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc<1>(&bars->tmem_base, BN);
-    tmem_relinquish<1>();
+    tmem_alloc<CG>(&bars->tmem_base, kAccStages * BN);
+    tmem_relinquish<CG>();
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 1) __syncthreads();
+  else cluster_sync();  // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   return *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
 }
 
-__device__ __forceinline__ void tile_teardown(uint32_t tmem_acc, int warp) {
+template <int CG>
+__device__ __forceinline__ void kernel_teardown(uint32_t tmem_base, int warp) {
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 1) __syncthreads();
+  else cluster_sync();  // no CTA of the pair may exit while the other can still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_acc, BN);
+    tmem_dealloc<CG>(tmem_base, kAccStages * BN);
   }
 }
 
-// grouped rasterisation: consecutive CTAs walk down 16 row tiles before moving to the next column tile, so the
-// ~300 co-resident CTAs share a compact set of operand rows in L2
-__device__ __forceinline__ void decode_tile(int id, int nti, int ntj, int& ti, int& tj) {
-  constexpr int GM = 16;
+// the epilogue warp has finished reading accumulator `acc`: hand it back to the MMA issuer (leader CTA)
+template <int CG>
+__device__ __forceinline__ void release_accumulator(PipeBarriers* bars, int acc, uint32_t rank, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    if (CG == 1 || rank == 0) mbar_arrive(&bars->tmem_empty[acc]);
+    else mbar_arrive_cluster(&bars->tmem_empty[acc], 0);
+  }
+}
+
+// grouped rasterisation: consecutive tiles walk down 8 row tiles before moving to the next column tile, so the
+// CTAs running at the same time share a compact set of operand rows in L2
+__device__ __forceinline__ void decode_grouped(int id, int nti, int ntj, int& ti, int& tj) {
+  constexpr int GM = 8;
   const int per_group = GM * ntj;
   const int group = id / per_group;
   const int first = group * GM;
@@ -152,22 +228,6 @@ __device__ __forceinline__ void decode_tile(int id, int nti, int ntj, int& ti, i
   const int r = id - group * per_group;
   ti = first + r % gm;
   tj = r / gm;
-}
-
-// Reduce-scatter over the 32 lanes of a warp: on entry every lane holds 32 values (one per column of a 32-column
-// chunk, for its own row); on exit lane l holds the sum over the 32 rows of column l.  31 shuffles.
-__device__ __forceinline__ float warp_column_sums(float (&e)[32], int lane) {
-#pragma unroll
-  for (int w = 16; w >= 1; w >>= 1) {
-    const bool up = (lane & w) != 0;
-#pragma unroll
-    for (int k = 0; k < w; ++k) {
-      const float send = up ? e[k] : e[k + w];
-      const float keep = up ? e[k + w] : e[k];
-      e[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-    }
-  }
-  return e[0];
 }
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -181,105 +241,241 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-constexpr uint32_t kEpiBarrier = 1;   // named barrier of the 128 epilogue threads
-constexpr uint32_t kEpiThreads = 128;
+// ---- fragment algebra of tmem_ld_block32 (ptx.cuh): element i of thread `lane` is
+//        row 16 (i >> 4) + 8 ((i >> 1) & 1) + lane / 4,   column 8 ((i >> 2) & 3) + 2 (lane % 4) + (i & 1)
+//      i.e. every thread owns 4 rows x 8 columns of the 32 x 32 block.
+__device__ __forceinline__ int frag_row(int i, int lane) { return 16 * (i >> 4) + 8 * ((i >> 1) & 1) + (lane >> 2); }
+__device__ __forceinline__ int frag_col(int i, int lane) { return 8 * ((i >> 2) & 3) + 2 * (lane & 3) + (i & 1); }
+
+// Column sums of a 32 x 32 block: 24 in-thread adds (4 rows per column), then a reduce-scatter of the 8 column partials
+// over the 8 threads that share lane % 4 (7 shuffles).  Returns the sum over the 32 rows of block column `col`.
+__device__ __forceinline__ float frag_column_sum(const float (&e)[32], int lane, int& col) {
+  float cp[8];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      cp[2 * n + c] = (e[4 * n + c] + e[4 * n + 2 + c]) + (e[16 + 4 * n + c] + e[16 + 4 * n + 2 + c]);
+#pragma unroll
+  for (int w = 16, half = 4; half >= 1; w >>= 1, half >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int k = 0; k < half; ++k) {
+      const float send = up ? cp[k] : cp[k + half];
+      const float keep = up ? cp[k + half] : cp[k];
+      cp[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  col = 8 * (idx >> 1) + 2 * (lane & 3) + (idx & 1);
+  return cp[0];
+}
+
+// In-thread row partials of a block: rp[2 g + h] += sum over the thread's 8 columns of row 16 g + 8 h + lane / 4.
+__device__ __forceinline__ void frag_row_partials(const float (&e)[32], float (&rp)[4]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int o = 16 * g + 2 * h;
+      rp[2 * g + h] += ((e[o] + e[o + 1]) + (e[o + 4] + e[o + 5])) + ((e[o + 8] + e[o + 9]) + (e[o + 12] + e[o + 13]));
+    }
+}
+
+// Reduce-scatter of the 4 row partials over the 4 threads of a quad (3 shuffles): returns the complete sum of
+// block row `row`.
+__device__ __forceinline__ float frag_row_sum(float (&rp)[4], int lane, int& row) {
+  {
+    const bool up = (lane & 1) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float send = up ? rp[k] : rp[k + 2];
+      const float keep = up ? rp[k + 2] : rp[k];
+      rp[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+  }
+  {
+    const bool up = (lane & 2) != 0;
+    const float send = up ? rp[0] : rp[1];
+    const float keep = up ? rp[1] : rp[0];
+    rp[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  row = 16 * (lane & 1) + 8 * ((lane >> 1) & 1) + (lane >> 2);
+  return rp[0];
+}
+
+constexpr uint32_t kBarAll = 1;     // named barrier of all epilogue threads
+constexpr uint32_t kBarSlice = 2;   // + slice: the 128 threads (4 warps, one per lane quarter) of one column slice
 
 // ============================================================================================== forward tiles
-__global__ void __launch_bounds__(kTileThreads, 2) forward_tiles_kernel(const __grid_constant__ FwdParams P) {
+template <int CG>
+__device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj) {
+  Tile r;
+  const int per_pair = nti_c * ntj;
+  r.job = t / per_pair;
+  decode_grouped(t - r.job * per_pair, nti_c, ntj, r.ti, r.tj);
+  r.m0 = r.ti * Geo<CG>::kTileM;
+  r.n0 = r.tj * BN;
+  r.split = 0;
+  return r;
+}
+
+template <int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __grid_constant__ FwdParams P) {
+  constexpr int S = EW / 4;        // column slices
+  constexpr int CS = BN / S;       // columns per slice
+  constexpr int NCH = CS / 32;     // 32-column chunks per warp
+  constexpr uint32_t kEpiThreads = 32 * EW;
   __shared__ PipeBarriers bars;
-  __shared__ float colacc[4][BN];
-  __shared__ float red4[4];
+  __shared__ float colacc[kAccStages][4][BN];
+  __shared__ float rowacc[kAccStages][S][BM];
+  __shared__ float redw[kAccStages][kMaxEpiWarps];
   uint8_t* smem = aligned_dyn_smem();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int p = blockIdx.y;
-  int ti, tj;
-  decode_tile(blockIdx.x, P.nti, P.ntj, ti, tj);
-  const int m0 = ti * BM, n0 = tj * BN;
-  const Job& job = P.jobs[p];
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+  const int nti_c = P.nti / CG;
+  const int total = 3 * nti_c * P.ntj;
 
-  const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
+  const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == 0) {
-    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars);
+    if (lane == 0) {
+      RingState rs;
+      for (int t = cluster_id; t < total; t += num_clusters) {
+        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
+      }
+    }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc);
+    if (lane == 0 && rank == 0) {
+      RingState rs;
+      int it = 0;
+      for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+        const int acc = it & 1;
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+      }
+    }
     __syncwarp();
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int epi_tid = q * 32 + lane;
-    const float s = expf(P.t3[p]);
-    const float c = s * kLog2e * P.acc_scale;  // accumulator -> logit in log2 units
-    const int row = m0 + q * 32 + lane;        // local row
-    const bool row_ok = row < P.rows_local;
-    const bool edge = (m0 + BM > P.rows_local) || (n0 + BN > P.rows_global);
-    const int diag_col = P.row_offset + row - n0;  // tile column holding this row's positive pair
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int slice = (warp - 2) >> 2;   // which CS accumulator columns
+    const int epi_tid = (warp - 2) * 32 + lane;
+    const int col0 = slice * CS;
+    int it = 0;
+    for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+      const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+      const int acc = it & 1;
+      const int p = tile.job;
+      const int ti = tile.ti * CG + static_cast<int>(rank);  // 128-row tile index of this CTA
+      const int tj = tile.tj;
+      const int m0 = ti * BM, n0 = tile.n0;
+      const float s = expf(P.t3[p]);
+      const float c = s * kLog2e * P.acc_scale;  // accumulator -> logit in log2 units
+      const int wrow0 = m0 + q * 32;             // first local row of this warp's block
+      const bool edge = (m0 + BM > P.rows_local) || (n0 + BN > P.rows_global);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
 
-    mbar_wait_bounded(&bars.tmem_full, 0, 3);
-    tc_fence_after();
+      mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
+      tc_fence_after();
 
-    // exponent reference of this tile, in log2 units.  s < 64: |logit| <= s (cosines), so exp(logit) and its sums are
-    // normal fp32 numbers without any shift; otherwise the true maximum of the tile is taken in a first pass over TMEM.
-    float ref2 = 0.f;
-    if (!(s < kFastPathMaxScale)) {
-      float mx = -INFINITY;
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + ch * 32, v);
-        tmem_ld_wait();
+      // exponent reference of this tile, in log2 units.  s < 64: |logit| <= s (cosines), so exp(logit) and its sums
+      // are normal fp32 numbers without any shift; otherwise the true maximum of the tile is taken in a first pass.
+      float ref2 = 0.f;
+      if (!(s < kFastPathMaxScale)) {
+        float mx = -INFINITY;
+        for (int ch = 0; ch < NCH; ++ch) {
+          uint32_t v[32];
+          tmem_ld_block32(taddr + ch * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const bool ok = !edge || (row_ok && (n0 + ch * 32 + k) < P.rows_global);
-          mx = fmaxf(mx, ok ? __uint_as_float(v[k]) : -INFINITY);
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = !edge || ((wrow0 + frag_row(i, lane)) < P.rows_local &&
+                                      (n0 + col0 + ch * 32 + frag_col(i, lane)) < P.rows_global);
+            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
+          }
+        }
+        mx = warp_max(mx);
+        if (lane == 0) redw[acc][warp - 2] = mx;
+        named_bar_sync(kBarAll, kEpiThreads);
+#pragma unroll
+        for (int w = 0; w < EW; ++w) mx = fmaxf(mx, redw[acc][w]);
+        ref2 = mx * c;
+      }
+
+      float rp[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t va[32];
+      [[maybe_unused]] uint32_t vb[32];
+      auto process = [&](uint32_t (&v)[32], int ch) {
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), c, -ref2));
+        const int gcol0 = n0 + col0 + ch * 32;          // first global column of the block
+        if (edge) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!((wrow0 + frag_row(i, lane)) < P.rows_local && (gcol0 + frag_col(i, lane)) < P.rows_global)) e[i] = 0.f;
+        }
+        const int grow0 = P.row_offset + wrow0;         // global index of the block's first row
+        if (grow0 < gcol0 + 32 && gcol0 < grow0 + 32) {  // the block touches the diagonal: positive-pair logits
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (grow0 + frag_row(i, lane) == gcol0 + frag_col(i, lane) && (wrow0 + frag_row(i, lane)) < P.rows_local)
+              P.diag[static_cast<size_t>(p) * P.rows_local + wrow0 + frag_row(i, lane)] =
+                  __uint_as_float(v[i]) * s * P.acc_scale;
+        }
+        frag_row_partials(e, rp);
+        int col;
+        const float csum = frag_column_sum(e, lane, col);
+        colacc[acc][q][col0 + ch * 32 + col] = csum;
+      };
+      if constexpr (EW == 8) {
+        // software pipeline: the TMEM load of chunk ch + 1 is in flight while chunk ch is processed
+        tmem_ld_block32(taddr, va);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_wait();
+          if (ch & 1) {
+            if (ch + 1 < NCH) tmem_ld_block32(taddr + (ch + 1) * 32, va);
+            process(vb, ch);
+          } else {
+            if (ch + 1 < NCH) tmem_ld_block32(taddr + (ch + 1) * 32, vb);
+            process(va, ch);
+          }
+        }
+      } else {  // 16 warps: four warps per scheduler hide the load latency, registers are the scarcer resource
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+          tmem_ld_block32(taddr + ch * 32, va);
+          tmem_ld_wait();
+          process(va, ch);
         }
       }
-      mx = warp_max(mx);
-      if (lane == 0) red4[q] = mx;
-      named_bar_sync(kEpiBarrier, kEpiThreads);
-      mx = fmaxf(fmaxf(red4[0], red4[1]), fmaxf(red4[2], red4[3]));
-      ref2 = mx * c;
-    }
-
-    float rowsum = 0.f;
-    float dval = 0.f;
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr + ch * 32, v);
-      tmem_ld_wait();
-      float e[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) e[k] = ex2_approx(fmaf(__uint_as_float(v[k]), c, -ref2));
-      if (edge) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if (!(row_ok && (n0 + ch * 32 + k) < P.rows_global)) e[k] = 0.f;
+      release_accumulator<CG>(&bars, acc, rank, lane);  // all TMEM reads of this warp are complete
+      {
+        int r;
+        const float rsum = frag_row_sum(rp, lane, r);
+        rowacc[acc][slice][q * 32 + r] = rsum;
       }
-      if ((diag_col >> 5) == ch) {  // at most one chunk per warp (diag_col - lane is warp-uniform)
-#pragma unroll
-        for (int k = 0; k < 32; ++k)
-          if ((diag_col & 31) == k) dval = __uint_as_float(v[k]);
+      named_bar_sync(kBarAll, kEpiThreads);
+      for (int cc = epi_tid; cc < BN; cc += kEpiThreads) {
+        if (n0 + cc < P.rows_global)
+          P.col_part[(static_cast<size_t>(p) * P.nti + ti) * P.rows_global + n0 + cc] =
+              (colacc[acc][0][cc] + colacc[acc][1][cc]) + (colacc[acc][2][cc] + colacc[acc][3][cc]);
       }
+      if (epi_tid < BM && m0 + epi_tid < P.rows_local) {
+        float rs = 0.f;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) rowsum += e[k];
-      colacc[q][ch * 32 + lane] = warp_column_sums(e, lane);
+        for (int u = 0; u < S; ++u) rs += rowacc[acc][u][epi_tid];
+        P.row_part[(static_cast<size_t>(p) * P.ntj + tj) * P.rows_local + m0 + epi_tid] = rs;
+      }
+      if (epi_tid == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ref2 / kLog2e;
     }
-    if (row_ok) {
-      P.row_part[(static_cast<size_t>(p) * P.ntj + tj) * P.rows_local + row] = rowsum;
-      if (diag_col >= 0 && diag_col < BN) P.diag[static_cast<size_t>(p) * P.rows_local + row] = dval * s * P.acc_scale;
-    }
-    named_bar_sync(kEpiBarrier, kEpiThreads);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int cc = epi_tid + h * 128;
-      if (n0 + cc < P.rows_global)
-        P.col_part[(static_cast<size_t>(p) * P.nti + ti) * P.rows_global + n0 + cc] =
-            (colacc[0][cc] + colacc[1][cc]) + (colacc[2][cc] + colacc[3][cc]);
-    }
-    if (epi_tid == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ref2 / kLog2e;
   }
-  tile_teardown(tmem_acc, warp);
+  kernel_teardown<CG>(tmem_base, warp);
 }
 
 // ============================================================================================== backward tiles
@@ -288,177 +484,249 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2) backward_tiles_kernel(const __grid_constant__ BwdParams P) {
+constexpr int kSlabBytes = BM * 64 * 2;  // one 128-row x 64-column fp16 slab of G' (16 KiB)
+
+template <int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) backward_tiles_kernel(const __grid_constant__ BwdParams P) {
+  constexpr int S = EW / 4;
+  constexpr int CS = BN / S;
+  constexpr int NSLAB = CS / 64;   // 64-column slabs per slice
+  constexpr uint32_t kEpiThreads = 32 * EW;
   __shared__ PipeBarriers bars;
-  __shared__ float colfac[BN];
-  __shared__ float red4[4];
+  __shared__ __align__(8) float colfac[kAccStages][BN];
+  __shared__ float redw[kAccStages][kMaxEpiWarps];
   uint8_t* smem = aligned_dyn_smem();
+  uint8_t* staging = smem + P.stages * Geo<CG>::kStageBytes;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int p = blockIdx.y;
-  int ti, tj;
-  decode_tile(blockIdx.x, P.nti, P.ntj, ti, tj);
-  const int m0 = ti * BM, n0 = tj * BN;
-  const Job& job = P.jobs[p];
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+  const int nti_c = P.nti / CG;
+  const int total = 3 * nti_c * P.ntj;
 
-  const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
+  const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == 0) {
-    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars);
+    if (lane == 0) {
+      RingState rs;
+      for (int t = cluster_id; t < total; t += num_clusters) {
+        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
+      }
+    }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc);
+    if (lane == 0 && rank == 0) {
+      RingState rs;
+      int it = 0;
+      for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+        const int acc = it & 1;
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+      }
+    }
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int epi_tid = q * 32 + lane;
-    const float s = expf(P.t3[p]);
-    const float c = s * kLog2e * P.acc_scale;
+    const int slice = (warp - 2) >> 2;
+    const int epi_tid = (warp - 2) * 32 + lane;
+    const int slice_tid = epi_tid & 127;
+    const int col0 = slice * CS;
     // c_p = s_p g_p / max_q |s_q g_q|
-    float mx = 0.f;
+    float mxsg = 0.f;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
-    const float cp = mx > 0.f ? (s * P.g3[p]) / mx : 0.f;
-    const float half_kc = 0.5f * kKappa * cp;
-    const bool fast = s < kFastPathMaxScale;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < P.rows_local;
-    const int diag_col = P.row_offset + row - n0;
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    const bool has_lo = P.store_map_lo[p] >= 0;
+    for (int r = 0; r < 3; ++r) mxsg = fmaxf(mxsg, fabsf(expf(P.t3[r]) * P.g3[r]));
+    int it = 0;
+    for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+      const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+      const int acc = it & 1;
+      const int p = tile.job;
+      const int ti = tile.ti * CG + static_cast<int>(rank);
+      const int tj = tile.tj;
+      const int m0 = ti * BM, n0 = tile.n0;
+      const float s = expf(P.t3[p]);
+      const float c = s * kLog2e * P.acc_scale;
+      const float cp = mxsg > 0.f ? (s * P.g3[p]) / mxsg : 0.f;
+      const float half_kc = 0.5f * kKappa * cp;
+      const bool fast = s < kFastPathMaxScale;
+      const int wrow0 = m0 + q * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
+      const bool has_lo = P.store_map_lo[p] >= 0;
+      const CUtensorMap* map_hi = &P.maps[P.store_map[p]];
+      const CUtensorMap* map_lo = has_lo ? &P.maps[P.store_map_lo[p]] : nullptr;
 
-    // per-row / per-column softmax normalisers, prepared while the MMAs run
-    // fast path: reciprocal row / column sums of exp(logit); safe path: log-sum-exps in log2 units
-    const float* rown = fast ? P.row_inv : P.lse_row;
-    const float* coln = fast ? P.col_inv : P.lse_col;
-    const float rown_v = row_ok ? rown[static_cast<size_t>(p) * P.rows_local + row] : 0.f;
-    const float rowfac = fast ? rown_v : rown_v * kLog2e;
+      // per-row / per-column softmax normalisers, prepared while the MMAs of this tile run.
+      // fast path: (kappa c_p / 2) / sum of exp(logit); safe path: log-sum-exps in log2 units
+      const float* rown = fast ? P.row_inv : P.lse_row;
+      const float* coln = fast ? P.col_inv : P.lse_col;
+      const float nscale = fast ? half_kc : kLog2e;
+      float rf[4];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int cc = epi_tid + h * 128;
-      const float coln_v = (n0 + cc < P.rows_global) ? coln[static_cast<size_t>(p) * P.rows_global + n0 + cc] : 0.f;
-      colfac[cc] = fast ? coln_v : coln_v * kLog2e;
-    }
-    named_bar_sync(kEpiBarrier, kEpiThreads);
-
-    mbar_wait_bounded(&bars.tmem_full, 0, 3);
-    tc_fence_after();
-    // all TMA loads have landed and every MMA has completed: the pipeline stages are free to stage the G' tiles.
-    // layout: hi slabs at [0, 32 KiB) (two 16 KiB buffers), lo slabs at [32 KiB, 64 KiB)
-    float dtacc = 0.f;
-    const CUtensorMap* map_hi = &P.maps[P.store_map[p]];
-    const CUtensorMap* map_lo = has_lo ? &P.maps[P.store_map_lo[p]] : nullptr;
-    const int r_in_tile = q * 32 + lane;
-
-    for (int sl = 0; sl < BN / 64; ++sl) {
-      const int b = sl & 1;
-      uint8_t* stage_hi = smem + b * 16384;
-      uint8_t* stage_lo = smem + 32768 + b * 16384;
-      if (sl >= 2) {
-        if (epi_tid == 0) tma_store_wait_read<1>();  // the store issued two slabs ago has finished reading buffer b
-        named_bar_sync(kEpiBarrier, kEpiThreads);
+      for (int j = 0; j < 4; ++j) {
+        const int row = wrow0 + 16 * (j >> 1) + 8 * (j & 1) + (lane >> 2);
+        rf[j] = (row < P.rows_local ? rown[static_cast<size_t>(p) * P.rows_local + row] : 0.f) * nscale;
       }
+      for (int cc = epi_tid; cc < BN; cc += kEpiThreads)
+        colfac[acc][cc] =
+            ((n0 + cc < P.rows_global) ? coln[static_cast<size_t>(p) * P.rows_global + n0 + cc] : 0.f) * nscale;
+      named_bar_sync(kBarAll, kEpiThreads);
+
+      mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
+      tc_fence_after();
+      float dtacc = 0.f;
 #pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
-        const int ch = sl * 2 + hc;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        float g[32];
-        if (fast) {
+      for (int sl = 0; sl < NSLAB; ++sl) {
+        // f16: every slab of the tile has its own staging buffer (reused one tile later); f16x3: one hi and one lo
+        // buffer per slice, reused by each of its slabs
+        uint8_t* stage_hi = staging + (has_lo ? slice * 2 : slice * NSLAB + sl) * kSlabBytes;
+        uint8_t* stage_lo = staging + (slice * 2 + 1) * kSlabBytes;
+        if (slice_tid == 0) {
+          if (has_lo || NSLAB == 1) tma_store_wait_read<0>();
+          else tma_store_wait_read<NSLAB - 1>();
+        }
+        named_bar_sync(kBarSlice + slice, 128);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const float a = __uint_as_float(v[k]);
-            const float e = ex2_approx(a * c);
-            g[k] = (e * (rowfac + colfac[ch * 32 + k])) * half_kc;
+        for (int hc = 0; hc < 2; ++hc) {
+          const int ch = sl * 2 + hc;  // 32-column chunk inside this slice
+          uint32_t v[32];
+          tmem_ld_block32(taddr + ch * 32, v);
+          float cf[8];
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float2 f = *reinterpret_cast<const float2*>(&colfac[acc][col0 + ch * 32 + 8 * n + 2 * (lane & 3)]);
+            cf[2 * n] = f.x;
+            cf[2 * n + 1] = f.y;
           }
-        } else {
+          tmem_ld_wait();
+          if (sl == NSLAB - 1 && hc == 1) release_accumulator<CG>(&bars, acc, rank, lane);  // last TMEM read
+          float g[32];
+          if (fast) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const float a = __uint_as_float(v[k]);
-            const float l2 = a * c;
-            g[k] = (ex2_approx(l2 - rowfac) + ex2_approx(l2 - colfac[ch * 32 + k])) * half_kc;
+            for (int i = 0; i < 32; ++i) {
+              const float e = ex2_approx(__uint_as_float(v[i]) * c);
+              g[i] = e * (rf[2 * (i >> 4) + ((i >> 1) & 1)] + cf[2 * ((i >> 2) & 3) + (i & 1)]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float l2 = __uint_as_float(v[i]) * c;
+              g[i] = (ex2_approx(l2 - rf[2 * (i >> 4) + ((i >> 1) & 1)]) +
+                      ex2_approx(l2 - cf[2 * ((i >> 2) & 3) + (i & 1)])) * half_kc;
+            }
+          }
+          const int gcol0 = n0 + col0 + ch * 32;
+          const int grow0 = P.row_offset + wrow0;
+          if (grow0 < gcol0 + 32 && gcol0 < grow0 + 32) {  // the block touches the diagonal: - kappa c_p I
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (grow0 + frag_row(i, lane) == gcol0 + frag_col(i, lane)) g[i] -= kKappa * cp;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dtacc = fmaf(g[i], __uint_as_float(v[i]), dtacc);
+          // fp16 pack + swizzled staging (128-byte rows, 16-byte chunk index XOR row & 7 == TMA SWIZZLE_128B);
+          // the four threads of a quad fill one 16-byte chunk
+#pragma unroll
+          for (int gh = 0; gh < 4; ++gh) {
+            const int r_in_tile = q * 32 + 16 * (gh >> 1) + 8 * (gh & 1) + (lane >> 2);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              const int i0 = 16 * (gh >> 1) + 4 * n + 2 * (gh & 1);
+              const int chunk16 = hc * 4 + n;
+              const uint32_t off = r_in_tile * 128 + ((chunk16 ^ (r_in_tile & 7)) << 4) + 4 * (lane & 3);
+              *reinterpret_cast<uint32_t*>(stage_hi + off) = pack_half2(g[i0], g[i0 + 1]);
+              if (has_lo) {
+                const float l0 = g[i0] - __half2float(__float2half_rn(g[i0]));
+                const float l1 = g[i0 + 1] - __half2float(__float2half_rn(g[i0 + 1]));
+                *reinterpret_cast<uint32_t*>(stage_lo + off) = pack_half2(l0, l1);
+              }
+            }
           }
         }
-        if ((diag_col >> 5) == ch) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if ((diag_col & 31) == k) g[k] -= kKappa * cp;
-        }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) dtacc = fmaf(g[k], __uint_as_float(v[k]), dtacc);
-        // fp16 pack + swizzled staging (128-byte rows, 16-byte chunk index XOR row & 7 == TMA SWIZZLE_128B)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 w;
-          w.x = pack_half2(g[j * 8 + 0], g[j * 8 + 1]);
-          w.y = pack_half2(g[j * 8 + 2], g[j * 8 + 3]);
-          w.z = pack_half2(g[j * 8 + 4], g[j * 8 + 5]);
-          w.w = pack_half2(g[j * 8 + 6], g[j * 8 + 7]);
-          const int chunk16 = hc * 4 + j;
-          const uint32_t off = r_in_tile * 128 + ((chunk16 ^ (r_in_tile & 7)) << 4);
-          *reinterpret_cast<uint4*>(stage_hi + off) = w;
-          if (has_lo) {
-            float lo[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) lo[t] = g[j * 8 + t] - __half2float(__float2half_rn(g[j * 8 + t]));
-            uint4 wl;
-            wl.x = pack_half2(lo[0], lo[1]);
-            wl.y = pack_half2(lo[2], lo[3]);
-            wl.z = pack_half2(lo[4], lo[5]);
-            wl.w = pack_half2(lo[6], lo[7]);
-            *reinterpret_cast<uint4*>(stage_lo + off) = wl;
+        fence_proxy_async_smem();
+        named_bar_sync(kBarSlice + slice, 128);
+        const int gcol = n0 + col0 + sl * 64;
+        if (slice_tid == 0) {
+          if (gcol < P.rows_global) {
+            tma_store_2d(map_hi, stage_hi, gcol, m0);
+            if (has_lo) tma_store_2d(map_lo, stage_lo, gcol, m0);
           }
+          tma_store_commit();
         }
       }
-      fence_proxy_async_smem();
-      named_bar_sync(kEpiBarrier, kEpiThreads);
-      if (epi_tid == 0 && (n0 + sl * 64) < P.rows_global) {
-        tma_store_2d(map_hi, stage_hi, n0 + sl * 64, m0);
-        if (has_lo) tma_store_2d(map_lo, stage_lo, n0 + sl * 64, m0);
-        tma_store_commit();
+      dtacc = warp_sum(dtacc);
+      if (lane == 0) redw[acc][warp - 2] = dtacc;
+      named_bar_sync(kBarAll, kEpiThreads);
+      if (epi_tid == 0) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < EW; ++w) sum += redw[acc][w];
+        P.dt_part[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = sum * P.acc_scale;
       }
     }
-    dtacc = warp_sum(dtacc);
-    if (lane == 0) red4[q] = dtacc;
-    named_bar_sync(kEpiBarrier, kEpiThreads);
-    if (epi_tid == 0) {
-      P.dt_part[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ((red4[0] + red4[1]) + (red4[2] + red4[3])) * P.acc_scale;
-      tma_store_wait_all<0>();
-    }
+    if (slice_tid == 0) tma_store_wait_all<0>();
   }
-  tile_teardown(tmem_acc, warp);
+  kernel_teardown<CG>(tmem_base, warp);
 }
 
 // ============================================================================================== plain GEMM tiles
-__global__ void __launch_bounds__(kTileThreads, 2) gemm_tiles_kernel(const __grid_constant__ GemmParams P) {
+template <int CG>
+__device__ __forceinline__ Tile decode_gemm(const GemmParams& P, int t) {
+  Tile r;
+  int j = 0;
+#pragma unroll
+  for (int u = 1; u < kMaxJobs; ++u)
+    if (u < P.njobs && t >= P.jobs[u].tile_base) j = u;
+  const Job& job = P.jobs[j];
+  const int local = t - job.tile_base;
+  const int tn = local % job.n_tiles;  // n fastest: the tiles sharing an A row panel run together
+  const int rest = local / job.n_tiles;
+  r.job = j;
+  r.split = rest % job.ksplits;
+  r.ti = rest / job.ksplits;
+  r.tj = tn;
+  r.m0 = r.ti * Geo<CG>::kTileM;
+  r.n0 = tn * BN;
+  return r;
+}
+
+template <int CG, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __grid_constant__ GemmParams P) {
+  constexpr int S = EW / 4;
+  constexpr int CS = BN / S;
+  constexpr int NCH = CS / 32;
   __shared__ PipeBarriers bars;
   uint8_t* smem = aligned_dyn_smem();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  int j = 0;
-#pragma unroll
-  for (int t = 1; t < kMaxJobs; ++t)
-    if (t < P.njobs && static_cast<int>(blockIdx.x) >= P.jobs[t].tile_base) j = t;
-  const Job& job = P.jobs[j];
-  const int local = blockIdx.x - job.tile_base;
-  const int tn = local % job.n_tiles;  // n fastest: the CTAs sharing an A row panel run together
-  const int rest = local / job.n_tiles;
-  const int split = rest % job.ksplits;
-  const int tm = rest / job.ksplits;
-  const int m0 = tm * BM, n0 = tn * BN;
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+  const int total = P.total_tiles;
 
-  const uint32_t tmem_acc = tile_setup(&bars, warp, lane);
+  const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == 0) {
-    if (lane == 0) producer_loop(P.maps, job, m0, n0, smem, &bars, split, job.ksplits);
+    if (lane == 0) {
+      RingState rs;
+      for (int t = cluster_id; t < total; t += num_clusters) {
+        const Tile tile = decode_gemm<CG>(P, t);
+        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
+      }
+    }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) mma_loop(job, smem, &bars, tmem_acc, split, job.ksplits);
+    if (lane == 0 && rank == 0) {
+      RingState rs;
+      int it = 0;
+      for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+        const Tile tile = decode_gemm<CG>(P, t);
+        const int acc = it & 1;
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+      }
+    }
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const bool accumulate_out = job.ksplits > 1;
+    const int slice = (warp - 2) >> 2;
     float alpha = P.alpha0;
     if (P.t3 != nullptr) {
       float mx = 0.f;
@@ -466,86 +734,125 @@ __global__ void __launch_bounds__(kTileThreads, 2) gemm_tiles_kernel(const __gri
       for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
       alpha *= mx;
     }
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < P.m[j];
-    const int ncols = P.n[j];
-    float* out = P.out[j] + static_cast<size_t>(row) * P.ldc[j] + n0;
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    mbar_wait_bounded(&bars.tmem_full, 0, 3);
-    tc_fence_after();
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(taddr + ch * 32, v);
-      tmem_ld_wait();
-      if (row_ok) {
+    int it = 0;
+    for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+      const Tile tile = decode_gemm<CG>(P, t);
+      const int acc = it & 1;
+      const int j = tile.job;
+      const bool accumulate_out = P.jobs[j].ksplits > 1;
+      const int row = tile.m0 + static_cast<int>(rank) * BM + q * 32 + lane;
+      const bool row_ok = row < P.m[j];
+      const int ncols = P.n[j];
+      const int c0 = tile.n0 + slice * CS;
+      float* out = P.out[j] + static_cast<size_t>(row) * P.ldc[j] + c0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + slice * CS;
+      mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
+      tc_fence_after();
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const int col = n0 + ch * 32 + k4 * 4;
-          if (col + 3 < ncols) {
-            float4 o;
-            o.x = __uint_as_float(v[k4 * 4 + 0]) * alpha;
-            o.y = __uint_as_float(v[k4 * 4 + 1]) * alpha;
-            o.z = __uint_as_float(v[k4 * 4 + 2]) * alpha;
-            o.w = __uint_as_float(v[k4 * 4 + 3]) * alpha;
-            float* dst = out + ch * 32 + k4 * 4;
-            if (!accumulate_out) {
-              *reinterpret_cast<float4*>(dst) = o;
-            } else {  // k-split chunks are combined with round-to-nearest fp32 adds in L2
-              red_add_f32(dst + 0, o.x);
-              red_add_f32(dst + 1, o.y);
-              red_add_f32(dst + 2, o.z);
-              red_add_f32(dst + 3, o.w);
+      for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == NCH - 1) release_accumulator<CG>(&bars, acc, rank, lane);
+        if (row_ok) {
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const int col = c0 + ch * 32 + k4 * 4;
+            if (col + 3 < ncols) {
+              float4 o;
+              o.x = __uint_as_float(v[k4 * 4 + 0]) * alpha;
+              o.y = __uint_as_float(v[k4 * 4 + 1]) * alpha;
+              o.z = __uint_as_float(v[k4 * 4 + 2]) * alpha;
+              o.w = __uint_as_float(v[k4 * 4 + 3]) * alpha;
+              float* dst = out + ch * 32 + k4 * 4;
+              if (!accumulate_out) {
+                *reinterpret_cast<float4*>(dst) = o;
+              } else {  // k-split chunks are combined with round-to-nearest fp32 adds in L2
+                red_add_f32(dst + 0, o.x);
+                red_add_f32(dst + 1, o.y);
+                red_add_f32(dst + 2, o.z);
+                red_add_f32(dst + 3, o.w);
+              }
             }
           }
         }
       }
     }
   }
-  tile_teardown(tmem_acc, warp);
+  kernel_teardown<CG>(tmem_base, warp);
 }
 
-template <class K>
-int prepare_kernel(K kernel) {
-  static bool done = false;  // per kernel instantiation; attribute is per device but all devices of a process match
-  static int last_dev = -1;
-  int dev = 0;
-  SCLIP_CUDA_OK(cudaGetDevice(&dev));
-  if (!done || dev != last_dev) {
-    SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-    SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    done = true;
-    last_dev = dev;
+// ---------------------------------------------------------------------------------------------- host launchers
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached = n;
   }
+  return cached;
+}
+
+template <class Params>
+int launch_persistent(void (*kernel)(Params), const Params& p, int cg, int ew, int smem_bytes, int total_cluster_tiles,
+                      cudaStream_t stream) {
+  SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  int clusters = sm_count() / cg;
+  if (total_cluster_tiles < clusters) clusters = total_cluster_tiles;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * cg, 1, 1);
+  cfg.blockDim = dim3(64 + 32 * ew, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   return SCLIP_OK;
 }
+
+// dispatch on the two compile-time knobs (CTA group 1 | 2, epilogue warps 8 | 16)
+#define SCLIP_DISPATCH(KERNEL, ...)                                                    \
+  do {                                                                                 \
+    if (cg == 2 && ew == 16) return launch_persistent(KERNEL<2, 16>, p, 2, 16, __VA_ARGS__); \
+    if (cg == 2) return launch_persistent(KERNEL<2, 8>, p, 2, 8, __VA_ARGS__);           \
+    if (ew == 16) return launch_persistent(KERNEL<1, 16>, p, 1, 16, __VA_ARGS__);        \
+    return launch_persistent(KERNEL<1, 8>, p, 1, 8, __VA_ARGS__);                        \
+  } while (0)
 
 }  // namespace
 
-int launch_forward_tiles(const FwdParams& p, cudaStream_t stream) {
-  int rc = prepare_kernel(forward_tiles_kernel);
-  if (rc) return rc;
-  dim3 grid(p.nti * p.ntj, 3, 1);
-  forward_tiles_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(p);
-  SCLIP_CUDA_OK(cudaGetLastError());
-  return SCLIP_OK;
+int staging_slabs(int ew, bool split) { return split ? (ew / 4) * 2 : 4; }
+
+int tile_smem_bytes(int cg, int stages, int slabs) {
+  const int stage_bytes = cg == 2 ? Geo<2>::kStageBytes : Geo<1>::kStageBytes;
+  return stages * stage_bytes + slabs * kSlabBytes + 1024;
 }
 
-int launch_backward_tiles(const BwdParams& p, cudaStream_t stream) {
-  int rc = prepare_kernel(backward_tiles_kernel);
-  if (rc) return rc;
-  dim3 grid(p.nti * p.ntj, 3, 1);
-  backward_tiles_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(p);
-  SCLIP_CUDA_OK(cudaGetLastError());
-  return SCLIP_OK;
+int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream) {
+  const int smem = tile_smem_bytes(cg, p.stages, 0);
+  const int total = 3 * (p.nti / cg) * p.ntj;
+  SCLIP_DISPATCH(forward_tiles_kernel, smem, total, stream);
 }
 
-int launch_gemm(const GemmParams& p, cudaStream_t stream) {
-  int rc = prepare_kernel(gemm_tiles_kernel);
-  if (rc) return rc;
-  dim3 grid(p.total_tiles, 1, 1);
-  gemm_tiles_kernel<<<grid, kTileThreads, kTileSmemBytes, stream>>>(p);
-  SCLIP_CUDA_OK(cudaGetLastError());
-  return SCLIP_OK;
+int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t stream) {
+  const int smem = tile_smem_bytes(cg, p.stages, staging_slabs(ew, p.store_map_lo[0] >= 0));
+  const int total = 3 * (p.nti / cg) * p.ntj;
+  SCLIP_DISPATCH(backward_tiles_kernel, smem, total, stream);
+}
+
+int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream) {
+  const int smem = tile_smem_bytes(cg, p.stages, 0);
+  const int total = p.total_tiles;
+  SCLIP_DISPATCH(gemm_tiles_kernel, smem, total, stream);
 }
 
 }  // namespace sclip

@@ -74,9 +74,9 @@ class _Workspace:
     def __init__(self, pb: Problem, device: torch.device):
         self.pb = pb
         self.lay = _lib.plan(pb)
-        self.blob = torch.empty(int(self.lay.total_bytes), dtype=torch.uint8, device=device)
-        if self.blob.data_ptr() % 256:
-            raise _lib.SclipError("allocator returned a workspace that is not 256-byte aligned")
+        raw = torch.empty(int(self.lay.total_bytes) + 256, dtype=torch.uint8, device=device)
+        skew = (-raw.data_ptr()) % 256  # the ABI wants a 256-byte aligned blob
+        self.blob = raw[skew:skew + int(self.lay.total_bytes)]
 
     def view(self, offset: int, shape, dtype: torch.dtype) -> torch.Tensor:
         n = 1
@@ -166,7 +166,7 @@ def workspace_bytes(rows_local: int, dim: int, dtype=torch.bfloat16, world: int 
 
 def _check_inputs(img, txt, aud):
     for name, e in (("image", img), ("text", txt), ("audio", aud)):
-        if not e.is_cuda:
+        if not e.is_cuda and not _BACKEND.allows_cpu:
             raise _lib.SclipError(
                 f"{name} embeddings are on {e.device}: the fused contrastive objective only runs on a CUDA (sm_100a) "
                 "device and has no CPU fallback")
@@ -174,18 +174,67 @@ def _check_inputs(img, txt, aud):
             raise ValueError("image / text / audio embeddings must share one (B, D) shape, dtype and device")
 
 
+class _CudaBackend:
+    """The product path: every stage is one call into libsclip.so on the current CUDA stream."""
+
+    allows_cpu = False
+
+    def __init__(self):
+        self._lib = None
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            self._lib = _lib.load()
+        return self._lib
+
+    def prologue(self, ws, img, txt, aud):
+        _lib.check(self.lib.sclip_prologue(byref(ws.pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _stream()),
+                   "sclip_prologue")
+
+    def forward_tiles(self, ws, t3):
+        _lib.check(self.lib.sclip_forward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_tiles")
+
+    def forward_reduce(self, ws):
+        _lib.check(self.lib.sclip_forward_reduce(byref(ws.pb), ws.ptr, _stream()), "sclip_forward_reduce")
+
+    def forward_loss(self, ws, col_lse_all, loss3):
+        _lib.check(self.lib.sclip_forward_loss(byref(ws.pb), ws.ptr, _ptr(col_lse_all), _ptr(loss3), _stream()),
+                   "sclip_forward_loss")
+
+    def backward_tiles(self, ws, t3, g3):
+        _lib.check(self.lib.sclip_backward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
+                   "sclip_backward_tiles")
+
+    def backward_gemms(self, ws, t3, g3):
+        _lib.check(self.lib.sclip_backward_gemms(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
+                   "sclip_backward_gemms")
+
+    def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3):
+        _lib.check(
+            self.lib.sclip_backward_finish(byref(ws.pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3), _ptr(g3),
+                                           _ptr(col), ctypes.c_float(mult), _ptr(dimg), _ptr(dtxt), _ptr(daud),
+                                           int(out_f32), _ptr(dt3), _stream()),
+            "sclip_backward_finish")
+
+
+# The stage executor.  The package ships exactly one (CUDA); the world_size > 1 CPU tests substitute a test double
+# from tests/ to exercise the collective choreography below under the gloo backend.
+_BACKEND = _CudaBackend()
+
+
 def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) -> torch.Tensor:
-    lib = _lib.load()
-    pb, lay, st = ws.pb, ws.lay, _stream()
+    be = _BACKEND
+    pb, lay = ws.pb, ws.lay
     _mark("begin")
-    _lib.check(lib.sclip_prologue(byref(pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), st), "sclip_prologue")
+    be.prologue(ws, img, txt, aud)
     _mark("prologue")
     loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
     if pb.world == 1:
-        _lib.check(lib.sclip_forward_tiles(byref(pb), ws.ptr, _ptr(t3), st), "sclip_forward_tiles")
+        be.forward_tiles(ws, t3)
         _mark("forward_tiles")
-        _lib.check(lib.sclip_forward_reduce(byref(pb), ws.ptr, st), "sclip_forward_reduce")
-        _lib.check(lib.sclip_forward_loss(byref(pb), ws.ptr, None, _ptr(loss3), st), "sclip_forward_loss")
+        be.forward_reduce(ws)
+        be.forward_loss(ws, None, loss3)
         _mark("forward_finish")
         return loss3
     import torch.distributed as dist
@@ -197,31 +246,32 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) 
         bufs.append(ws.view(lay.xhat_lo, (3, bg, d), torch.float16))
     for buf in bufs:  # all-gather of the normalised row shards (each modality is column-side in one pair)
         for m in range(3):
-            dist.all_gather_into_tensor(buf[m], buf[m, off:off + bl], group=pg)
+            dist.all_gather_into_tensor(buf[m].view(-1), buf[m, off:off + bl].reshape(-1), group=pg)
     _mark("all_gather")
-    _lib.check(lib.sclip_forward_tiles(byref(pb), ws.ptr, _ptr(t3), st), "sclip_forward_tiles")
+    be.forward_tiles(ws, t3)
     _mark("forward_tiles")
-    _lib.check(lib.sclip_forward_reduce(byref(pb), ws.ptr, st), "sclip_forward_reduce")
+    be.forward_reduce(ws)
+    # column statistics: every rank holds the log-sum-exp over its own rows; merge them over ranks
     col_local = ws.view(lay.lse_col_local, (3, bg), torch.float32)
     col_all = torch.empty((pb.world, 3, bg), dtype=torch.float32, device=img.device)
-    dist.all_gather_into_tensor(col_all, col_local, group=pg)
-    _lib.check(lib.sclip_forward_loss(byref(pb), ws.ptr, _ptr(col_all), _ptr(loss3), st), "sclip_forward_loss")
+    dist.all_gather_into_tensor(col_all.view(-1), col_local.reshape(-1), group=pg)
+    be.forward_loss(ws, col_all, loss3)
     dist.all_reduce(loss3, group=pg)  # every rank reports the global-batch losses
     _mark("forward_finish")
     return loss3
 
 
 def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveConfig):
-    lib = _lib.load()
-    pb, lay, st = ws.pb, ws.lay, _stream()
+    be = _BACKEND
+    pb, lay = ws.pb, ws.lay
     out_f32 = 1 if (cfg.grads_fp32 or img.dtype == torch.float32) else 0
     gdtype = torch.float32 if out_f32 else img.dtype
     dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
     dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
     _mark("backward_begin")
-    _lib.check(lib.sclip_backward_tiles(byref(pb), ws.ptr, _ptr(t3), _ptr(g3), st), "sclip_backward_tiles")
+    be.backward_tiles(ws, t3, g3)
     _mark("backward_tiles")
-    _lib.check(lib.sclip_backward_gemms(byref(pb), ws.ptr, _ptr(t3), _ptr(g3), st), "sclip_backward_gemms")
+    be.backward_gemms(ws, t3, g3)
     _mark("backward_gemms")
     col = None
     mult = 1.0
@@ -232,14 +282,11 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
         part = ws.view(lay.dxhat_col, (3, bg, d), torch.float32)
         col = torch.empty((3, bl, d), dtype=torch.float32, device=img.device)
         for m in range(3):  # reduce-scatter of the column-role partial gradients
-            dist.reduce_scatter_tensor(col[m], part[m], group=cfg.process_group)
+            dist.reduce_scatter_tensor(col[m].view(-1), part[m].view(-1), group=cfg.process_group)
         _mark("reduce_scatter")
         if cfg.grad_scale == "ddp":
             mult = float(pb.world)
-    _lib.check(
-        lib.sclip_backward_finish(byref(pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3), _ptr(g3), _ptr(col),
-                                  ctypes.c_float(mult), _ptr(dimg), _ptr(dtxt), _ptr(daud), out_f32, _ptr(dt3), st),
-        "sclip_backward_finish")
+    be.backward_finish(ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3)
     _mark("backward_finish")
     if pb.world > 1 and cfg.grad_scale == "sum":
         import torch.distributed as dist

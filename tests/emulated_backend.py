@@ -1,0 +1,177 @@
+"""TEST DOUBLE -- a CPU (torch, fp64) stand-in for the seven CUDA stage calls of ``libsclip.so``.
+
+It exists only so that the world_size > 1 choreography in ``synergy_clip_b200.ops`` (all-gather of the
+normalised shards, merge of the column statistics, reduce-scatter of the column-role gradients, DDP
+gradient scaling) can run under the gloo backend on a machine without a GPU.  It reads and writes the
+same workspace sub-buffers, at the offsets ``sclip_plan`` reports, with the same meaning as the kernels
+(``include/sclip.h``); tile-level partials are collapsed into tile 0.  It is never importable from the
+package and is not a fallback: ``tests/test_multirank_cpu.py`` installs it explicitly.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+KAPPA = 32768.0
+PAIRS = ((0, 1), (1, 2), (2, 0))  # (row modality, column modality) of IT, TA, AI
+
+
+class EmulatedBackend:
+    allows_cpu = True
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _dims(ws):
+        pb = ws.pb
+        return pb.rows_local, pb.rows_global, pb.dim, pb.row_offset
+
+    @staticmethod
+    def _x3(ws):
+        return ws.pb.math == 1
+
+    def _xhat(self, ws):
+        """Operands as the tensor cores see them: fp16 values (hi + lo in the split mode), fp64 here."""
+        bl, bg, d, off = self._dims(ws)
+        hi = ws.view(ws.lay.xhat, (3, bg, d), torch.float16).double()
+        if self._x3(ws):
+            return (hi + ws.view(ws.lay.xhat_lo, (3, bg, d), torch.float16).double()) / 256.0
+        return hi
+
+    # ------------------------------------------------------------------ forward
+    def prologue(self, ws, img, txt, aud):
+        bl, bg, d, off = self._dims(ws)
+        hi = ws.view(ws.lay.xhat, (3, bg, d), torch.float16)
+        inv = ws.view(ws.lay.inv_norm, (3, bl), torch.float32)
+        for m, x in enumerate((img, txt, aud)):
+            x = x.float()
+            nrm = x.norm(dim=-1, keepdim=True)
+            inv[m] = (1.0 / nrm).squeeze(-1)
+            xh = x / nrm
+            if self._x3(ws):
+                scaled = xh * 256.0
+                h = scaled.half()
+                hi[m, off:off + bl] = h
+                ws.view(ws.lay.xhat_lo, (3, bg, d), torch.float16)[m, off:off + bl] = (scaled - h.float()).half()
+            else:
+                hi[m, off:off + bl] = xh.half()
+        ws.view(ws.lay.status, (4,), torch.int32).zero_()
+
+    def _logits(self, ws, t3, p):
+        bl, bg, d, off = self._dims(ws)
+        xh = self._xhat(ws)
+        r, c = PAIRS[p]
+        cos = xh[r, off:off + bl] @ xh[c].T
+        return cos, math.exp(float(t3[p])) * cos
+
+    def forward_tiles(self, ws, t3):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        row_part = ws.view(lay.row_part, (3, lay.col_tiles, bl), torch.float32).zero_()
+        col_part = ws.view(lay.col_part, (3, lay.row_tiles, bg), torch.float32).zero_()
+        tile_ref = ws.view(lay.tile_ref, (3, lay.row_tiles, lay.col_tiles), torch.float32)
+        diag = ws.view(lay.diag, (3, bl), torch.float32)
+        for p in range(3):
+            _, logits = self._logits(ws, t3, p)
+            ref = 0.0 if math.exp(float(t3[p])) < 64.0 else float(logits.max())
+            tile_ref[p] = ref
+            e = torch.exp(logits - ref)
+            row_part[p, 0] = e.sum(1).float()
+            col_part[p, 0] = e.sum(0).float()
+            diag[p] = logits[torch.arange(bl), off + torch.arange(bl)].float()
+
+    def forward_reduce(self, ws):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        row_part = ws.view(lay.row_part, (3, lay.col_tiles, bl), torch.float32).double()
+        col_part = ws.view(lay.col_part, (3, lay.row_tiles, bg), torch.float32).double()
+        ref = ws.view(lay.tile_ref, (3, lay.row_tiles, lay.col_tiles), torch.float32).double()[:, 0, 0]
+        rsum, csum = row_part.sum(1), col_part.sum(1)
+        ws.view(lay.lse_row, (3, bl), torch.float32).copy_(ref[:, None] + rsum.log())
+        ws.view(lay.lse_col_local, (3, bg), torch.float32).copy_(ref[:, None] + csum.log())
+        ws.view(lay.row_inv, (3, bl), torch.float32).copy_(1.0 / rsum)
+        ws.view(lay.col_sum_local, (3, bg), torch.float32).copy_(csum)
+
+    def forward_loss(self, ws, col_lse_all, loss3):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        lse_col = ws.view(lay.lse_col, (3, bg), torch.float32)
+        col_inv = ws.view(lay.col_inv, (3, bg), torch.float32)
+        if col_lse_all is None:
+            lse_col.copy_(ws.view(lay.lse_col_local, (3, bg), torch.float32))
+            col_inv.copy_(1.0 / ws.view(lay.col_sum_local, (3, bg), torch.float32))
+        else:
+            merged = torch.logsumexp(col_lse_all.double(), dim=0)
+            lse_col.copy_(merged)
+            col_inv.copy_(torch.exp(-merged))
+        lse_row = ws.view(lay.lse_row, (3, bl), torch.float32).double()
+        diag = ws.view(lay.diag, (3, bl), torch.float32).double()
+        part = ((lse_row - diag).sum(1) + (lse_col.double()[:, off:off + bl] - diag).sum(1)) / (2.0 * bg)
+        ws.view(lay.loss_part, (3,), torch.float32).copy_(part)
+        loss3.copy_(part)
+
+    # ------------------------------------------------------------------ backward
+    @staticmethod
+    def _coeffs(t3, g3):
+        sg = [math.exp(float(t)) * float(g) for t, g in zip(t3, g3)]
+        mx = max(abs(v) for v in sg)
+        return mx, [v / mx if mx > 0 else 0.0 for v in sg]
+
+    def backward_tiles(self, ws, t3, g3):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        _, cps = self._coeffs(t3, g3)
+        g_hi = ws.view(lay.grad_tiles, (3, bl, lay.ld_g), torch.float16)
+        dt_part = ws.view(lay.dt_part, (3, lay.row_tiles * lay.col_tiles), torch.float32).zero_()
+        lse_row = ws.view(lay.lse_row, (3, bl), torch.float32).double()
+        lse_col = ws.view(lay.lse_col, (3, bg), torch.float32).double()
+        for p in range(3):
+            cos, logits = self._logits(ws, t3, p)
+            soft = torch.exp(logits - lse_row[p][:, None]) + torch.exp(logits - lse_col[p][None, :])
+            gp = 0.5 * KAPPA * cps[p] * soft
+            gp[torch.arange(bl), off + torch.arange(bl)] -= KAPPA * cps[p]
+            dt_part[p, 0] = float((gp * cos).sum())
+            h = gp.half()
+            g_hi[p, :, :bg] = h
+            if self._x3(ws):
+                ws.view(lay.grad_tiles_lo, (3, bl, lay.ld_g), torch.float16)[p, :, :bg] = (gp - h.double()).half()
+
+    def _gprime(self, ws):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        g = ws.view(lay.grad_tiles, (3, bl, lay.ld_g), torch.float16)[:, :, :bg].double()
+        if self._x3(ws):
+            g = g + ws.view(lay.grad_tiles_lo, (3, bl, lay.ld_g), torch.float16)[:, :, :bg].double()
+        return g
+
+    def backward_gemms(self, ws, t3, g3):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        mx, _ = self._coeffs(t3, g3)
+        alpha = mx / (KAPPA * bg)
+        xh = self._xhat(ws)
+        g = self._gprime(ws)
+        row_out = ws.view(lay.dxhat_row, (3, bl, d), torch.float32)
+        for m in range(3):
+            pr, pc = m, (m + 2) % 3
+            acc = g[pr] @ xh[PAIRS[pr][1]]                              # row role, k = global row
+            col_role = g[pc].T @ xh[PAIRS[pc][0], off:off + bl]          # column role, k = local row -> (bg, d)
+            if ws.pb.world == 1:
+                row_out[m] = (alpha * (acc + col_role)).float()
+            else:
+                row_out[m] = (alpha * acc).float()
+                ws.view(lay.dxhat_col, (3, bg, d), torch.float32)[m] = (alpha * col_role).float()
+
+    def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        inv = ws.view(lay.inv_norm, (3, bl), torch.float32).double()
+        row_out = ws.view(lay.dxhat_row, (3, bl, d), torch.float32).double()
+        for m, (x, out) in enumerate(zip((img, txt, aud), (dimg, dtxt, daud))):
+            dd = row_out[m] + (col[m].double() if col is not None else 0.0)
+            xh = x.double() * inv[m][:, None]
+            dx = (dd - xh * (xh * dd).sum(-1, keepdim=True)) * inv[m][:, None] * mult
+            out.copy_(dx.to(out.dtype))
+        mx, _ = self._coeffs(t3, g3)
+        dt_part = ws.view(lay.dt_part, (3, lay.row_tiles * lay.col_tiles), torch.float32).double()
+        dt3.copy_((dt_part.sum(1) * mx / (KAPPA * bg) * mult).float())

@@ -28,6 +28,19 @@ WORKLOADS = {"north_star": (32768, 768), "cfg2": (8192, 512)}
 CPU_SAMPLE_ROWS = 4096  # bounded CPU sample: a 4096-row sub-batch of the same embeddings
 
 
+def load_traffic(b, d, world):
+    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed `ncu --set full` capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("rows_global") == b and t.get("dim") == d and t.get("world") == world:
+            return t.get("gemm_tiles_kernel_dram_bytes")
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -40,29 +53,49 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU (NVML, ~20 ms period; nvidia-smi as a fallback)
+    while the timed region runs."""
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, sm_max_mhz, power_w, reasons bitmask)
         self._stop = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), float(mx),
+                                 pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                 int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            self._stop.wait(0.02)
+
+    def _run_smi(self):
+        query = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+        bits = (0x8, 0x40, 0x20, 0x4)
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={query}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [x.strip() for x in out.strip().split(",")]
                 if len(parts) >= 7:
-                    self.samples.append(parts)
+                    mask = sum(b for b, v in zip(bits, parts[3:7]) if v.lower() == "active")
+                    self.samples.append((float(parts[0]), float(parts[1]), float(parts[2]), mask))
             except Exception:  # noqa: BLE001
                 pass
             self._stop.wait(0.1)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:  # noqa: BLE001
+            self._run_smi()
 
     def __enter__(self):
         self._thread.start()
@@ -74,14 +107,16 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = []
-        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), start=3):
-            if any(s[i].lower() == "active" for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s in self.samples:
+            mask |= s[3]
+        names = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                 (0x4, "sw_power_cap"))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1],
+                "reasons": [n for b, n in names if mask & b], "samples": len(sm),
+                "power_w_max": max(s[2] for s in self.samples)}
 
 
 def cpu_tail_rate(rows: int, dim: int, steps: int, warmup: int, seed: int = 1234):
@@ -321,7 +356,9 @@ def main():
             "gpu_launches": 8 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "gemm_tiles_kernel (backward_gemms)", "achieved": gemm_tf,
                          "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": (gemm_tf / peaks["bf16_tflops"]) if gemm_tf else None, "traffic": None,
+                         "frac": (gemm_tf / peaks["bf16_tflops"]) if gemm_tf else None,
+                         "traffic": load_traffic(b, d, world),
+                         "algorithmic_flops_per_launch": 12.0 * b * b * d / world,
                          "peak_source": peaks["source"] + ", burst figure",
                          "stage_ms": main_res["stages"], "stage_tflops": stage_tf},
             "cpu_baseline": cpu,

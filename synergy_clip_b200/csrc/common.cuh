@@ -110,6 +110,8 @@ struct FwdParams {
   int rows_local, rows_global, row_offset;
   int nti, ntj;     // layout strides: 128-row tiles (padded to even) and 256-column tiles
   int stages;       // depth of the TMA ring
+  int debug;        // profiling experiments only (SCLIP_DEBUG): 1 = epilogue releases the accumulator untouched,
+                    // 2 = epilogue only loads the accumulator from TMEM
   float acc_scale;  // accumulator -> cosine (1 in F16 mode, 2^-16 in F16X3 mode)
 };
 

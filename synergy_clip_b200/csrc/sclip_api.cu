@@ -341,6 +341,10 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
   p.nti = w.lay.row_tiles;
   p.ntj = w.lay.col_tiles;
   p.stages = ring_stages(0);
+  {
+    const char* e = getenv("SCLIP_DEBUG");
+    p.debug = e != nullptr ? atoi(e) : 0;
+  }
   p.acc_scale = w.pb.math == SCLIP_MATH_F16X3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
   return launch_forward_tiles(p, cta_group(), epi_warps(), static_cast<cudaStream_t>(stream));
 }

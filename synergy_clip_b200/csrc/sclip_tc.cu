@@ -381,6 +381,21 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
 
       mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
       tc_fence_after();
+      if (P.debug != 0) {  // profiling experiments: how long does the mainloop take without the epilogue?
+        if (P.debug == 2) {
+          uint32_t v[32];
+          uint32_t sink = 0;
+          for (int ch = 0; ch < NCH; ++ch) {
+            tmem_ld_block32(taddr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sink ^= v[i];
+          }
+          if (sink == 0x12345678u) P.tile_ref[0] = 1.f;
+        }
+        release_accumulator<CG>(&bars, acc, rank, lane);
+        continue;
+      }
 
       // exponent reference of this tile, in log2 units.  s < 64: |logit| <= s (cosines), so exp(logit) and its sums
       // are normal fp32 numbers without any shift; otherwise the true maximum of the tile is taken in a first pass.

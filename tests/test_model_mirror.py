@@ -111,7 +111,7 @@ def test_pretraining_step_on_gpu_matches_oracle(tiny_encoders):
     from synergy_clip_b200.model import Tri_CLIP
 
     b = 35  # the reference's per-GPU batch (main_pretraining.py:79)
-    m = Tri_CLIP(_tiny_config(is_pt=True)).cuda()
+    m = Tri_CLIP(_tiny_config(is_pt=True)).cuda().eval()  # eval: no dropout, so the embeddings can be recomputed
     batch = _batch(b, "cuda")
     out = m(**batch)
     alpha, beta, gamma = 0.15, 1.0, 1.0

@@ -43,7 +43,10 @@ int ring_stages(int slabs) {
   const int stage_bytes = cta_group() == 2 ? (A_STAGE_BYTES + B_STAGE_BYTES / 2) : STAGE_BYTES;
   const int budget = 227 * 1024 - 14 * 1024 - 1024 - slabs * 16384;  // static smem + alignment slack
   int st = budget / stage_bytes;
-  return st > 6 ? 6 : (st < 2 ? 2 : st);
+  st = st > 6 ? 6 : (st < 2 ? 2 : st);
+  const char* e = getenv("SCLIP_STAGES");  // profiling experiments only
+  if (e != nullptr && atoi(e) >= 1 && atoi(e) < st) st = atoi(e);
+  return st;
 }
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }

@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: run the collectives on the compute stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -267,7 +268,8 @@ def main():
         return full
 
     def measure(b, d, shard, steps, warmup):
-        cfg = ops.TriContrastiveConfig(process_group=pg if shard else None, math="f16", grad_scale="ddp")
+        cfg = ops.TriContrastiveConfig(process_group=pg if shard else None, math="f16", grad_scale="ddp",
+                                       overlap=not args.no_overlap)
         embs = make_inputs(b, d, shard)
         t3 = torch.full((3,), LOGIT_SCALE_INIT, device=dev)
         g3 = torch.ones(3, device=dev)

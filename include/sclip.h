@@ -113,6 +113,13 @@ int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, cons
  * written to memory.  Needs the complete `xhat` (after the all-gather when world > 1). */
 int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3, void* stream);
 
+/* Same, restricted to the pairs in pair_mask (bit 0 IT, bit 1 TA, bit 2 AI) and to the 256-column tiles
+ * [col_tile_begin, col_tile_end): lets the host run the tiles whose column operand has already arrived (this rank's
+ * own rows first, then one modality after the other) while the all-gather of the rest is still in flight.  Every
+ * (pair, column tile) must be covered exactly once before sclip_forward_reduce. */
+int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
+                             int col_tile_begin, int col_tile_end, void* stream);
+
 /* Merge the per-tile statistics into lse_row and lse_col_local. */
 int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream);
 
@@ -135,6 +142,18 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
  * dxhat_col[m] = G'_{colpair(m)}^T . xhat_{row modality} (rows_global x dim partial sums; world == 1: added
  *                into dxhat_row by the same accumulator instead). */
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
+
+/* Same, one role at a time (world > 1): SCLIP_ROLE_COLUMN writes only dxhat_col (so its reduce-scatter can start),
+ * SCLIP_ROLE_ROW only dxhat_row; SCLIP_ROLE_BOTH == sclip_backward_gemms. */
+#define SCLIP_ROLE_BOTH 0
+#define SCLIP_ROLE_COLUMN 1
+#define SCLIP_ROLE_ROW 2
+int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
+                              void* stream);
+
+/* Process-wide launch option: the persistent tile kernels use at most max_sms SMs (0 = all), leaving the rest to
+ * concurrently running communication kernels.  Returns the previous value. */
+int sclip_set_max_sms(int max_sms);
 
 /* Backward of the normalisation: d x = (d - xhat <xhat, d>) / ||x|| with d = dxhat_row (+ col_contrib, the
  * reduce-scattered column-role gradients [3][rows_local][dim] fp32, NULL when world == 1), times grad_mult

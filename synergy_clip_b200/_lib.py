@@ -45,10 +45,13 @@ _PROTOTYPES = {
     "sclip_plan": (c_int, [POINTER(Problem), POINTER(Layout)]),
     "sclip_prologue": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_forward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p]),
+    "sclip_forward_tiles_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "sclip_forward_reduce": (c_int, [POINTER(Problem), c_void_p, c_void_p]),
     "sclip_forward_loss": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_gemms": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sclip_backward_gemms_role": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "sclip_set_max_sms": (c_int, [c_int]),
     "sclip_backward_finish": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "sclip_forward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -109,6 +109,8 @@ struct FwdParams {
   float* diag;
   int rows_local, rows_global, row_offset;
   int nti, ntj;     // layout strides: 128-row tiles (padded to even) and 256-column tiles
+  int tj_begin, tj_count;  // column tiles this launch covers
+  int pair_list[3], npairs;  // pairs this launch covers
   int stages;       // depth of the TMA ring
   int debug;        // profiling experiments only (SCLIP_DEBUG): 1 = epilogue releases the accumulator untouched,
                     // 2 = epilogue only loads the accumulator from TMEM
@@ -155,6 +157,7 @@ int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t strea
 int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream);
 int cta_group();   // SCLIP_CTA_GROUP environment override (1 or 2), default 2
 int epi_warps();   // SCLIP_EPI_WARPS environment override (8 or 16), default 16
+int max_sms();     // sclip_set_max_sms (0 = all)
 int staging_slabs(int ew, bool split);  // 16 KiB G' staging slabs the backward tile kernel needs
 
 int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream);

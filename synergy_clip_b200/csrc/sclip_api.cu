@@ -27,11 +27,14 @@ int cta_group() {
   return cached;
 }
 
+static int g_max_sms = 0;
+int max_sms() { return g_max_sms; }
+
 int epi_warps() {
   static int cached = 0;
   if (cached == 0) {
     const char* e = getenv("SCLIP_EPI_WARPS");
-    cached = (e != nullptr && e[0] == '8') ? 8 : 16;
+    cached = (e != nullptr && e[0] == '1') ? 16 : 8;
   }
   return cached;
 }
@@ -320,12 +323,28 @@ int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, cons
   return launch_prologue(w, x3, st);
 }
 
+int sclip_set_max_sms(int n) {
+  const int prev = g_max_sms;
+  g_max_sms = n < 0 ? 0 : n;
+  return prev;
+}
+
 int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3, void* stream) {
+  return sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, stream);
+}
+
+int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
+                             int col_tile_begin, int col_tile_end, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
   if (t3 == nullptr) {
     set_error("t3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (col_tile_end > w.lay.col_tiles) col_tile_end = w.lay.col_tiles;
+  if (col_tile_begin < 0 || col_tile_begin > col_tile_end) {
+    set_error("bad column tile range [%d, %d)", col_tile_begin, col_tile_end);
     return SCLIP_ERR_ARGUMENT;
   }
   FwdParams p;
@@ -343,6 +362,10 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
   p.row_offset = w.pb.row_offset;
   p.nti = w.lay.row_tiles;
   p.ntj = w.lay.col_tiles;
+  p.tj_begin = col_tile_begin;
+  p.tj_count = col_tile_end - col_tile_begin;
+  for (int q = 0; q < 3; ++q)
+    if (pair_mask & (1 << q)) p.pair_list[p.npairs++] = q;
   p.stages = ring_stages(0);
   {
     const char* e = getenv("SCLIP_DEBUG");
@@ -402,6 +425,11 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
 }
 
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
+  return sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, stream);
+}
+
+int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
+                              void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -424,9 +452,14 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
   // chunks are combined with round-to-nearest fp32 adds (red.global.add.f32 into the zeroed output)
   auto splits_for = [&](int kb) { return x3 ? ceil_div(kb, 16) : 1; };
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (role < SCLIP_ROLE_BOTH || role > SCLIP_ROLE_ROW || (pb.world == 1 && role != SCLIP_ROLE_BOTH)) {
+    set_error("role=%d is invalid (single-rank problems only take SCLIP_ROLE_BOTH)", role);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const bool do_row = role != SCLIP_ROLE_COLUMN, do_col = pb.world > 1 && role != SCLIP_ROLE_ROW;
   if (x3) {
-    SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_row, 0, 3 * bl * d * 4, st));
-    if (pb.world > 1) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
+    if (do_row) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_row, 0, 3 * bl * d * 4, st));
+    if (do_col) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
   }
   int nj = 0, tiles = 0;
   auto add_role = [&](Job& job, int m, bool row_role) {
@@ -446,7 +479,7 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
       job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
     }
   };
-  for (int m = 0; m < 3; ++m) {
+  for (int m = 0; m < 3 && do_row; ++m) {
     Job& job = p.jobs[nj];
     add_role(job, m, true);
     if (pb.world == 1) add_role(job, m, false);
@@ -461,7 +494,7 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
     p.n[nj] = pb.dim;
     ++nj;
   }
-  if (pb.world > 1) {
+  if (do_col) {
     for (int m = 0; m < 3; ++m) {
       Job& job = p.jobs[nj];
       add_role(job, m, false);

@@ -311,11 +311,12 @@ constexpr uint32_t kBarSlice = 2;   // + slice: the 128 threads (4 warps, one pe
 
 // ============================================================================================== forward tiles
 template <int CG>
-__device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj) {
+__device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int tj_begin = 0) {
   Tile r;
   const int per_pair = nti_c * ntj;
   r.job = t / per_pair;
   decode_grouped(t - r.job * per_pair, nti_c, ntj, r.ti, r.tj);
+  r.tj += tj_begin;
   r.m0 = r.ti * Geo<CG>::kTileM;
   r.n0 = r.tj * BN;
   r.split = 0;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
   const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
   const int nti_c = P.nti / CG;
-  const int total = 3 * nti_c * P.ntj;
+  const int total = P.npairs * nti_c * P.tj_count;
 
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
@@ -346,7 +347,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
     if (lane == 0) {
       RingState rs;
       for (int t = cluster_id; t < total; t += num_clusters) {
-        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        tile.job = P.pair_list[tile.job];
         producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
       }
     }
@@ -356,7 +358,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
-        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        tile.job = P.pair_list[tile.job];
         const int acc = it & 1;
         mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
       }
@@ -369,7 +372,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
     const int col0 = slice * CS;
     int it = 0;
     for (int t = cluster_id; t < total; t += num_clusters, ++it) {
-      const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        tile.job = P.pair_list[tile.job];
       const int acc = it & 1;
       const int p = tile.job;
       const int ti = tile.ti * CG + static_cast<int>(rank);  // 128-row tile index of this CTA
@@ -816,7 +820,9 @@ template <class Params>
 int launch_persistent(void (*kernel)(Params), const Params& p, int cg, int ew, int smem_bytes, int total_cluster_tiles,
                       cudaStream_t stream) {
   SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  int clusters = sm_count() / cg;
+  int sms = sm_count();
+  if (max_sms() > 0 && max_sms() < sms) sms = max_sms();
+  int clusters = sms / cg;
   if (total_cluster_tiles < clusters) clusters = total_cluster_tiles;
   if (clusters < 1) clusters = 1;
   cudaLaunchConfig_t cfg;
@@ -856,7 +862,8 @@ int tile_smem_bytes(int cg, int stages, int slabs) {
 
 int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream) {
   const int smem = tile_smem_bytes(cg, p.stages, 0);
-  const int total = 3 * (p.nti / cg) * p.ntj;
+  const int total = p.npairs * (p.nti / cg) * p.tj_count;
+  if (total <= 0) return SCLIP_OK;
   SCLIP_DISPATCH(forward_tiles_kernel, smem, total, stream);
 }
 
@@ -869,6 +876,7 @@ int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t strea
 int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream) {
   const int smem = tile_smem_bytes(cg, p.stages, 0);
   const int total = p.total_tiles;
+  if (total <= 0) return SCLIP_OK;
   SCLIP_DISPATCH(gemm_tiles_kernel, smem, total, stream);
 }
 

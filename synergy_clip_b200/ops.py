@@ -36,9 +36,14 @@ class TriContrastiveConfig:
                               parameter gradients over ranks (main_pretraining.py:138);
                     "sum"  -> exact partial derivatives of the global-batch losses.
     grads_fp32    : emit fp32 embedding gradients even for bf16 inputs (used by the parity tests).
+    overlap       : world_size > 1 only.  Run the collectives on a side stream under the tile kernels: the similarity
+                    tiles start with this rank's own columns and then take the modalities in the order their
+                    all-gathers complete; the column-role gradient GEMMs run first so that their reduce-scatter
+                    overlaps the row-role GEMMs.  `comm_sms` SMs are left to the communication kernels meanwhile.
     """
 
-    def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False):
+    def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
+                 overlap: bool = True, comm_sms: int = 12):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -47,6 +52,8 @@ class TriContrastiveConfig:
         self.math = math
         self.grad_scale = grad_scale
         self.grads_fp32 = grads_fp32
+        self.overlap = overlap
+        self.comm_sms = comm_sms
 
 
 _DEFAULT = TriContrastiveConfig()
@@ -58,6 +65,20 @@ _TRACE = None
 def _mark(name: str) -> None:
     if _TRACE is not None:
         _TRACE(name)
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _COMM_STREAMS:
+        _COMM_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _COMM_STREAMS[key]
+
+
+def _sm_count(device: torch.device) -> int:
+    return torch.cuda.get_device_properties(device).multi_processor_count
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -195,6 +216,17 @@ class _CudaBackend:
     def forward_tiles(self, ws, t3):
         _lib.check(self.lib.sclip_forward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_tiles")
 
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi):
+        _lib.check(self.lib.sclip_forward_tiles_cols(byref(ws.pb), ws.ptr, _ptr(t3), int(pair_mask), int(tile_lo),
+                                                     int(tile_hi), _stream()), "sclip_forward_tiles_cols")
+
+    def backward_gemms_role(self, ws, t3, g3, role):
+        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), _stream()),
+                   "sclip_backward_gemms_role")
+
+    def set_max_sms(self, n):
+        return self.lib.sclip_set_max_sms(int(n))
+
     def forward_reduce(self, ws):
         _lib.check(self.lib.sclip_forward_reduce(byref(ws.pb), ws.ptr, _stream()), "sclip_forward_reduce")
 
@@ -244,11 +276,44 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) 
     bufs = [ws.view(lay.xhat, (3, bg, d), torch.float16)]
     if pb.math == MATH_F16X3:
         bufs.append(ws.view(lay.xhat_lo, (3, bg, d), torch.float16))
-    for buf in bufs:  # all-gather of the normalised row shards (each modality is column-side in one pair)
-        for m in range(3):
+
+    def gather(m):  # all-gather of the normalised row shards of modality m
+        for buf in bufs:
             dist.all_gather_into_tensor(buf[m].view(-1), buf[m, off:off + bl].reshape(-1), group=pg)
-    _mark("all_gather")
-    be.forward_tiles(ws, t3)
+
+    overlap = cfg.overlap and img.is_cuda and bl % 256 == 0
+    if not overlap:
+        for m in range(3):
+            gather(m)
+        _mark("all_gather")
+        be.forward_tiles(ws, t3)
+    else:
+        # Pair p needs the gathered column modality (p + 1) % 3.  Gather txt, aud, img in that order on the side stream;
+        # meanwhile run the tiles whose columns are this rank's own rows, then pair IT, TA, AI as their operands land.
+        cur = torch.cuda.current_stream()
+        comm = _comm_stream(img.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        landed = []
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            for m in (1, 2, 0):
+                gather(m)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                landed.append(ev)
+        lo, hi = off // 256, (off + bl) // 256
+        prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
+        try:
+            be.forward_tiles_cols(ws, t3, 7, lo, hi)
+            for p, ev in enumerate(landed):
+                cur.wait_event(ev)
+                if p == 2:
+                    be.set_max_sms(prev)  # nothing left in flight: use every SM again
+                be.forward_tiles_cols(ws, t3, 1 << p, 0, lo)
+                be.forward_tiles_cols(ws, t3, 1 << p, hi, lay.col_tiles)
+        finally:
+            be.set_max_sms(prev)
     _mark("forward_tiles")
     be.forward_reduce(ws)
     # column statistics: every rank holds the log-sum-exp over its own rows; merge them over ranks
@@ -271,19 +336,46 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     _mark("backward_begin")
     be.backward_tiles(ws, t3, g3)
     _mark("backward_tiles")
-    be.backward_gemms(ws, t3, g3)
-    _mark("backward_gemms")
     col = None
     mult = 1.0
-    if pb.world > 1:
+    if pb.world == 1:
+        be.backward_gemms(ws, t3, g3)
+        _mark("backward_gemms")
+    else:
         import torch.distributed as dist
 
         bl, bg, d = pb.rows_local, pb.rows_global, pb.dim
         part = ws.view(lay.dxhat_col, (3, bg, d), torch.float32)
         col = torch.empty((3, bl, d), dtype=torch.float32, device=img.device)
-        for m in range(3):  # reduce-scatter of the column-role partial gradients
-            dist.reduce_scatter_tensor(col[m].view(-1), part[m].view(-1), group=cfg.process_group)
-        _mark("reduce_scatter")
+
+        def scatter():  # reduce-scatter of the column-role partial gradients
+            for m in range(3):
+                dist.reduce_scatter_tensor(col[m].view(-1), part[m].view(-1), group=cfg.process_group)
+
+        if not (cfg.overlap and img.is_cuda):
+            be.backward_gemms(ws, t3, g3)
+            _mark("backward_gemms")
+            scatter()
+            _mark("reduce_scatter")
+        else:
+            cur = torch.cuda.current_stream()
+            comm = _comm_stream(img.device)
+            be.backward_gemms_role(ws, t3, g3, 1)  # column role first ...
+            done = torch.cuda.Event()
+            done.record(cur)
+            col.record_stream(comm)
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                scatter()                            # ... its reduce-scatter runs under the row-role GEMMs
+                reduced = torch.cuda.Event()
+                reduced.record(comm)
+            prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
+            try:
+                be.backward_gemms_role(ws, t3, g3, 2)
+            finally:
+                be.set_max_sms(prev)
+            cur.wait_event(reduced)
+            _mark("backward_gemms")
         if cfg.grad_scale == "ddp":
             mult = float(pb.world)
     be.backward_finish(ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3)

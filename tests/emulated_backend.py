@@ -65,20 +65,33 @@ class EmulatedBackend:
         return cos, math.exp(float(t3[p])) * cos
 
     def forward_tiles(self, ws, t3):
+        self.forward_tiles_cols(ws, t3, 7, 0, ws.lay.col_tiles)
+
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi):
+        """Column tiles [tile_lo, tile_hi) of the pairs in pair_mask; row partials land in slot `tile_lo`."""
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
-        row_part = ws.view(lay.row_part, (3, lay.col_tiles, bl), torch.float32).zero_()
-        col_part = ws.view(lay.col_part, (3, lay.row_tiles, bg), torch.float32).zero_()
+        if tile_hi <= tile_lo:
+            return
+        row_part = ws.view(lay.row_part, (3, lay.col_tiles, bl), torch.float32)
+        col_part = ws.view(lay.col_part, (3, lay.row_tiles, bg), torch.float32)
         tile_ref = ws.view(lay.tile_ref, (3, lay.row_tiles, lay.col_tiles), torch.float32)
         diag = ws.view(lay.diag, (3, bl), torch.float32)
+        c0, c1 = tile_lo * 256, min(tile_hi * 256, bg)
         for p in range(3):
+            if not pair_mask & (1 << p):
+                continue
             _, logits = self._logits(ws, t3, p)
-            ref = 0.0 if math.exp(float(t3[p])) < 64.0 else float(logits.max())
+            # one reference for the whole pair (the kernels use one per tile; any consistent choice merges the same)
+            ref = 0.0 if math.exp(float(t3[p])) < 64.0 else float(math.exp(float(t3[p])))
             tile_ref[p] = ref
-            e = torch.exp(logits - ref)
-            row_part[p, 0] = e.sum(1).float()
-            col_part[p, 0] = e.sum(0).float()
-            diag[p] = logits[torch.arange(bl), off + torch.arange(bl)].float()
+            e = torch.exp(logits[:, c0:c1] - ref)
+            row_part[p, tile_lo + 1:tile_hi] = 0.0
+            row_part[p, tile_lo] = e.sum(1).float()
+            col_part[p, :, c0:c1] = 0.0
+            col_part[p, 0, c0:c1] = e.sum(0).float()
+            if c0 <= off < c1:
+                diag[p] = logits[torch.arange(bl), off + torch.arange(bl)].float()
 
     def forward_reduce(self, ws):
         bl, bg, d, off = self._dims(ws)
@@ -144,7 +157,13 @@ class EmulatedBackend:
             g = g + ws.view(lay.grad_tiles_lo, (3, bl, lay.ld_g), torch.float16)[:, :, :bg].double()
         return g
 
+    def set_max_sms(self, n):
+        return 0
+
     def backward_gemms(self, ws, t3, g3):
+        self.backward_gemms_role(ws, t3, g3, 0)
+
+    def backward_gemms_role(self, ws, t3, g3, role):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
         mx, _ = self._coeffs(t3, g3)
@@ -159,8 +178,10 @@ class EmulatedBackend:
             if ws.pb.world == 1:
                 row_out[m] = (alpha * (acc + col_role)).float()
             else:
-                row_out[m] = (alpha * acc).float()
-                ws.view(lay.dxhat_col, (3, bg, d), torch.float32)[m] = (alpha * col_role).float()
+                if role in (0, 2):
+                    row_out[m] = (alpha * acc).float()
+                if role in (0, 1):
+                    ws.view(lay.dxhat_col, (3, bg, d), torch.float32)[m] = (alpha * col_role).float()
 
     def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3):
         bl, bg, d, off = self._dims(ws)

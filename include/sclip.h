@@ -88,6 +88,11 @@ typedef struct sclip_layout {
   uint64_t dxhat_row;     /* [3][rows_local][dim] fp32 d/dxhat from the row role (+ column role if world==1) */
   uint64_t dxhat_col;     /* [3][rows_global][dim] fp32 column-role partial sums (world > 1 only)
                              [exchange: reduce-scatter sum over ranks]                                        */
+  uint64_t diag_all;      /* [3][rows_global] fp32 positive-pair logits of ALL rows (stash scaling); sclip_forward_diag
+                             writes this rank's rows [exchange: all-gather when world > 1]                     */
+  uint64_t fac_row;       /* [3][2][rows_local] fp32 row factors of the stash -> G' conversion                 */
+  uint64_t fac_col;       /* [3][2][rows_global] fp32 column factors                                           */
+  uint64_t dot_part;      /* [3][ceil(rows_local/8)] fp32 partial sums of <xhat, dxhat> (stash mode dlogit_scale) */
   uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed) */
   int32_t row_tiles;      /* ceil(rows_local / 128)   */
   int32_t col_tiles;      /* ceil(rows_global / 256)  */
@@ -116,9 +121,16 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
 /* Same, restricted to the pairs in pair_mask (bit 0 IT, bit 1 TA, bit 2 AI) and to the 256-column tiles
  * [col_tile_begin, col_tile_end): lets the host run the tiles whose column operand has already arrived (this rank's
  * own rows first, then one modality after the other) while the all-gather of the rest is still in flight.  Every
- * (pair, column tile) must be covered exactly once before sclip_forward_reduce. */
+ * (pair, column tile) must be covered exactly once before sclip_forward_reduce.
+ * flags & SCLIP_FWD_STASH (SCLIP_MATH_F16 only): additionally store E~_ij = exp(L_ij - (L_ii + L_jj)/2) / 16 as fp16
+ * tiles into grad_tiles, so that the backward needs no recomputation of the similarities (sclip_backward_scale
+ * instead of sclip_backward_tiles).  Needs diag_all (sclip_forward_diag, all-gathered when world > 1). */
+#define SCLIP_FWD_STASH 1
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
-                             int col_tile_begin, int col_tile_end, void* stream);
+                             int col_tile_begin, int col_tile_end, int flags, void* stream);
+
+/* Positive-pair logits L_ii of this rank's rows for the three pairs, written into diag_all at row_offset. */
+int sclip_forward_diag(const sclip_problem* problem, void* ws, const float* t3, void* stream);
 
 /* Merge the per-tile statistics into lse_row and lse_col_local. */
 int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream);
@@ -137,6 +149,11 @@ int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_
  * as fp16 tiles, plus the per-tile partial sums of dL/dlogit_scale.  g3: upstream gradients of the three
  * losses (device). */
 int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
+
+/* The same tiles without recomputation, after a forward with SCLIP_FWD_STASH: in place on grad_tiles,
+ *   G'_ij = E~_ij (R1_i C1_j + R2_i C2_j)  (= kappa c_p (softmax_rows + softmax_cols)/2; the "- kappa c_p I" term is
+ * applied by sclip_backward_finish with SCLIP_BWD_STASHED).  HBM-bound elementwise pass. */
+int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
 /* dxhat_row[m] = G'_{rowpair(m)} . xhat_{col modality}   (rows_local x dim, complete)
  * dxhat_col[m] = G'_{colpair(m)}^T . xhat_{row modality} (rows_global x dim partial sums; world == 1: added
@@ -159,14 +176,18 @@ int sclip_set_max_sms(int max_sms);
  * reduce-scattered column-role gradients [3][rows_local][dim] fp32, NULL when world == 1), times grad_mult
  * (1, or world when the caller's DDP wrapper will average over ranks).  Also finishes dlogit_scale:
  * dt3[p] = grad_mult * (this rank's share), device, 3 floats.
- * dimg/dtxt/daud have the dtype of the problem unless out_f32 != 0. */
+ * dimg/dtxt/daud have the dtype of the problem unless out_f32 != 0.
+ * flags & SCLIP_BWD_STASHED: the tiles came from sclip_backward_scale (see there). */
+#define SCLIP_BWD_STASHED 1
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                           const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,
-                          void* dtxt, void* daud, int out_f32, float* dt3, void* stream);
+                          void* dtxt, void* daud, int out_f32, int flags, float* dt3, void* stream);
 
-/* ---- single-GPU convenience (world == 1): the whole tail in two calls --------------------------- */
+/* ---- single-GPU convenience (world == 1): the whole tail in two calls ---------------------------
+ * keep_for_backward != 0: sclip_backward will follow on the same workspace (SCLIP_MATH_F16 then stashes in the
+ * forward and skips the recomputation); 0: forward only (evaluation loops). */
 int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
-                  const float* t3, float* loss3, void* stream);
+                  const float* t3, int keep_for_backward, float* loss3, void* stream);
 int sclip_backward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                    const float* t3, const float* g3, void* dimg, void* dtxt, void* daud, int out_f32, float* dt3,
                    void* stream);

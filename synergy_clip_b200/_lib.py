@@ -32,7 +32,7 @@ class Layout(Structure):
     _fields_ = [(name, c_uint64) for name in (
         "total_bytes", "xhat", "xhat_lo", "inv_norm", "row_part", "col_part", "tile_ref", "diag", "lse_row",
         "lse_col_local", "lse_col", "row_inv", "col_sum_local", "col_inv", "loss_part", "grad_tiles", "grad_tiles_lo", "dt_part", "dxhat_row", "dxhat_col",
-        "status")] + [("row_tiles", c_int32), ("col_tiles", c_int32), ("ld_g", c_int32), ("reserved", c_int32)]
+        "diag_all", "fac_row", "fac_col", "dot_part", "status")] + [("row_tiles", c_int32), ("col_tiles", c_int32), ("ld_g", c_int32), ("reserved", c_int32)]
 
 
 class SclipError(RuntimeError):
@@ -45,7 +45,9 @@ _PROTOTYPES = {
     "sclip_plan": (c_int, [POINTER(Problem), POINTER(Layout)]),
     "sclip_prologue": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_forward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p]),
-    "sclip_forward_tiles_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sclip_forward_tiles_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sclip_forward_diag": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p]),
+    "sclip_backward_scale": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_forward_reduce": (c_int, [POINTER(Problem), c_void_p, c_void_p]),
     "sclip_forward_loss": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -53,8 +55,9 @@ _PROTOTYPES = {
     "sclip_backward_gemms_role": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sclip_set_max_sms": (c_int, [c_int]),
     "sclip_backward_finish": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "sclip_forward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sclip_forward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                              c_void_p]),
     "sclip_backward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "sclip_gemm_f16": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int,

@@ -96,6 +96,10 @@ struct Workspace {  // resolved device pointers of one workspace blob
   float* dt_part;
   float* dxhat_row;
   float* dxhat_col;
+  float* diag_all;
+  float* fac_row;
+  float* fac_col;
+  float* dot_part;
   int* status;
 };
 
@@ -111,6 +115,9 @@ struct FwdParams {
   int nti, ntj;     // layout strides: 128-row tiles (padded to even) and 256-column tiles
   int tj_begin, tj_count;  // column tiles this launch covers
   int pair_list[3], npairs;  // pairs this launch covers
+  int stash;                 // also store E~ = exp(L_ij - (L_ii + L_jj)/2)/16 as fp16 tiles (backward without recompute)
+  int store_map[3];          // tensor maps (box 64 x 128) of the stash strips
+  const float* diag_all;     // [3][rows_global] positive-pair logits (stash scaling)
   int stages;       // depth of the TMA ring
   int debug;        // profiling experiments only (SCLIP_DEBUG): 1 = epilogue releases the accumulator untouched,
                     // 2 = epilogue only loads the accumulator from TMEM
@@ -164,7 +171,9 @@ int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t st
 int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream);
 int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream);
 int launch_backward_finish(const Workspace& w, const void* const x3[3], const float* t3, const float* g3,
-                           const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, float* dt3,
-                           cudaStream_t stream);
+                           const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, int stash,
+                           float* dt3, cudaStream_t stream);
+int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream);
+int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream);
 
 }  // namespace sclip

@@ -124,6 +124,10 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->dt_part = take(3 * nti * ntj * 4);
   lay->dxhat_row = take(3 * bl * d * 4);
   lay->dxhat_col = pb->world > 1 ? take(3 * bg * d * 4) : lay->dxhat_row;
+  lay->diag_all = take(3 * bg * 4);
+  lay->fac_row = take(3 * 2 * bl * 4);
+  lay->fac_col = take(3 * 2 * bg * 4);
+  lay->dot_part = take(3 * ((bl + 7) / 8) * 4);
   lay->status = take(4 * 4);
   lay->total_bytes = off;
   return SCLIP_OK;
@@ -162,6 +166,10 @@ int resolve(const sclip_problem* pb, void* ws, Workspace* w) {
   w->dt_part = reinterpret_cast<float*>(b + l.dt_part);
   w->dxhat_row = reinterpret_cast<float*>(b + l.dxhat_row);
   w->dxhat_col = reinterpret_cast<float*>(b + l.dxhat_col);
+  w->diag_all = reinterpret_cast<float*>(b + l.diag_all);
+  w->fac_row = reinterpret_cast<float*>(b + l.fac_row);
+  w->fac_col = reinterpret_cast<float*>(b + l.fac_col);
+  w->dot_part = reinterpret_cast<float*>(b + l.dot_part);
   w->status = reinterpret_cast<int*>(b + l.status);
   return SCLIP_OK;
 }
@@ -330,11 +338,33 @@ int sclip_set_max_sms(int n) {
 }
 
 int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3, void* stream) {
-  return sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, stream);
+  return sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, 0, stream);
+}
+
+int sclip_forward_diag(const sclip_problem* problem, void* ws, const float* t3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr) {
+    set_error("t3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_diag(w, t3, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr || g3 == nullptr || w.pb.math != SCLIP_MATH_F16) {
+    set_error("sclip_backward_scale needs t3, g3 and a SCLIP_MATH_F16 problem");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_backward_scale(w, t3, g3, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
-                             int col_tile_begin, int col_tile_end, void* stream) {
+                             int col_tile_begin, int col_tile_end, int flags, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -366,7 +396,17 @@ int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float
   p.tj_count = col_tile_end - col_tile_begin;
   for (int q = 0; q < 3; ++q)
     if (pair_mask & (1 << q)) p.pair_list[p.npairs++] = q;
-  p.stages = ring_stages(0);
+  if (flags & SCLIP_FWD_STASH) {
+    if (w.pb.math != SCLIP_MATH_F16) {
+      set_error("SCLIP_FWD_STASH is only defined for SCLIP_MATH_F16");
+      return SCLIP_ERR_ARGUMENT;
+    }
+    p.stash = 1;
+    p.diag_all = w.diag_all;
+    for (int q = 0; q < 3; ++q) p.store_map[q] = tab.use(kGK + q);
+    if (tab.rc) return tab.rc;
+  }
+  p.stages = ring_stages(p.stash ? 4 : 0);
   {
     const char* e = getenv("SCLIP_DEBUG");
     p.debug = e != nullptr ? atoi(e) : 0;
@@ -519,7 +559,7 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
 
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                           const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,
-                          void* dtxt, void* daud, int out_f32, float* dt3, void* stream) {
+                          void* dtxt, void* daud, int out_f32, int flags, float* dt3, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -534,20 +574,30 @@ int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* im
     set_error("world > 1 needs the reduce-scattered column-role gradients (col_contrib)");
     return SCLIP_ERR_ARGUMENT;
   }
-  return launch_backward_finish(w, x3, t3, g3, col_contrib, grad_mult, dx3, out_f32, dt3,
-                                static_cast<cudaStream_t>(stream));
+  if (t3 == nullptr || g3 == nullptr) {
+    set_error("t3 / g3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_backward_finish(w, x3, t3, g3, col_contrib, grad_mult, dx3, out_f32, (flags & SCLIP_BWD_STASHED) ? 1 : 0,
+                                dt3, static_cast<cudaStream_t>(stream));
 }
 
+// the single-GPU convenience calls remember, per workspace, whether the last forward stashed
+static thread_local const void* g_stashed_ws = nullptr;
+
 int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
-                  const float* t3, float* loss3, void* stream) {
+                  const float* t3, int keep_for_backward, float* loss3, void* stream) {
   if (problem != nullptr && problem->world != 1) {
     set_error("sclip_forward is the single-GPU entry point (world must be 1); use the stage calls when sharded");
     return SCLIP_ERR_ARGUMENT;
   }
+  const bool stash = keep_for_backward && problem != nullptr && problem->math == SCLIP_MATH_F16;
   int rc = sclip_prologue(problem, ws, img, txt, aud, stream);
-  if (!rc) rc = sclip_forward_tiles(problem, ws, t3, stream);
+  if (!rc && stash) rc = sclip_forward_diag(problem, ws, t3, stream);
+  if (!rc) rc = sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, stash ? SCLIP_FWD_STASH : 0, stream);
   if (!rc) rc = sclip_forward_reduce(problem, ws, stream);
   if (!rc) rc = sclip_forward_loss(problem, ws, nullptr, loss3, stream);
+  if (!rc) g_stashed_ws = stash ? ws : (g_stashed_ws == ws ? nullptr : g_stashed_ws);
   return rc;
 }
 
@@ -558,11 +608,13 @@ int sclip_backward(const sclip_problem* problem, void* ws, const void* img, cons
     set_error("sclip_backward is the single-GPU entry point (world must be 1); use the stage calls when sharded");
     return SCLIP_ERR_ARGUMENT;
   }
-  int rc = sclip_backward_tiles(problem, ws, t3, g3, stream);
+  const bool stashed = ws != nullptr && g_stashed_ws == ws;
+  int rc = stashed ? sclip_backward_scale(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
+  if (stashed) g_stashed_ws = nullptr;  // the stash is consumed in place
   if (!rc) rc = sclip_backward_gemms(problem, ws, t3, g3, stream);
   if (!rc)
-    rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32, dt3,
-                               stream);
+    rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32,
+                               stashed ? SCLIP_BWD_STASHED : 0, dt3, stream);
   return rc;
 }
 

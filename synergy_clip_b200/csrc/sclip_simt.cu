@@ -33,6 +33,16 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
 __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -222,81 +232,240 @@ struct FinishArgs {
   const float* dxhat_row;    // [3][rows][dim]
   const float* col_contrib;  // [3][rows][dim] or null
   const float* inv_norm;
-  int rows, dim;
+  const __half* xhat[3];     // normalised operands at this rank's rows (stash mode: the -I term of G' is applied here)
+  const float* t3;
+  const float* g3;
+  float* dot_part;           // [3][gridDim.x] per-block sums of <xhat, dxhat_total> (stash mode: dlogit_scale)
+  int rows, dim, rows_global;
+  int stash;
   float grad_mult;
 };
 
-// d x = (d - xhat <xhat, d>) / ||x||, with xhat recomputed in fp32 from the caller's embeddings
+// d x = (d - xhat <xhat, d>) / ||x||, with xhat recomputed in fp32 from the caller's embeddings.
+// Stash mode: the tiles handed to the gradient GEMMs were kappa c_p (softmax_rows + softmax_cols)/2 without the
+// "- kappa c_p I" term, whose contribution -(s_p g_p / B) xhat_partner is subtracted here, and
+// <xhat_m, dxhat_total_m> = dt_{rowpair(m)} + dt_{colpair(m)} is accumulated for dlogit_scale.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(kRowsPerBlock * 32) backward_finish_kernel(const FinishArgs a) {
+  __shared__ float blockdot[kRowsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kRowsPerBlock + warp;
   const int m = blockIdx.y;
-  if (row >= a.rows) return;
-  const size_t base = (static_cast<size_t>(m) * a.rows + row) * a.dim;
-  const T* xr = static_cast<const T*>(a.x[m]) + static_cast<size_t>(row) * a.dim;
-  TO* outr = static_cast<TO*>(a.dx[m]) + static_cast<size_t>(row) * a.dim;
-  const float inv = a.inv_norm[static_cast<size_t>(m) * a.rows + row];
   float dot = 0.f;
-  for (int i = lane * 8; i < a.dim; i += 256) {
-    float x[8], d[8];
-    load8(xr + i, x);
-    load8(a.dxhat_row + base + i, d);
-    if (a.col_contrib != nullptr) {
-      float e[8];
-      load8(a.col_contrib + base + i, e);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) d[k] += e[k];
+  if (row < a.rows) {
+    const size_t base = (static_cast<size_t>(m) * a.rows + row) * a.dim;
+    const T* xr = static_cast<const T*>(a.x[m]) + static_cast<size_t>(row) * a.dim;
+    TO* outr = static_cast<TO*>(a.dx[m]) + static_cast<size_t>(row) * a.dim;
+    const float inv = a.inv_norm[static_cast<size_t>(m) * a.rows + row];
+    // modality m is row-side in pair m (partner = column modality (m+1)%3) and column-side in pair (m+2)%3
+    // (partner = its row modality (m+2)%3)
+    const int m1 = (m + 1) % 3, m2 = (m + 2) % 3;
+    float k1 = 0.f, k2 = 0.f;
+    if (a.stash) {
+      k1 = expf(a.t3[m]) * a.g3[m] / static_cast<float>(a.rows_global);
+      k2 = expf(a.t3[m2]) * a.g3[m2] / static_cast<float>(a.rows_global);
     }
-    float part = 0.f;
+    const __half* p1 = a.xhat[m1] + static_cast<size_t>(row) * a.dim;
+    const __half* p2 = a.xhat[m2] + static_cast<size_t>(row) * a.dim;
+    auto total = [&](int i, float (&d)[8]) {
+      load8(a.dxhat_row + base + i, d);
+      if (a.col_contrib != nullptr) {
+        float e[8];
+        load8(a.col_contrib + base + i, e);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) part = fmaf(x[k] * inv, d[k], part);
-    dot += part;
+        for (int k = 0; k < 8; ++k) d[k] += e[k];
+      }
+      if (a.stash) {
+        float y1[8], y2[8];
+        load8(p1 + i, y1);
+        load8(p2 + i, y2);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[k] -= k1 * y1[k] + k2 * y2[k];
+      }
+    };
+    for (int i = lane * 8; i < a.dim; i += 256) {
+      float x[8], d[8];
+      load8(xr + i, x);
+      total(i, d);
+      float part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part = fmaf(x[k] * inv, d[k], part);
+      dot += part;
+    }
+    dot = warp_sum_f(dot);
+    const float scale = inv * a.grad_mult;
+    for (int i = lane * 8; i < a.dim; i += 256) {
+      float x[8], d[8], o[8];
+      load8(xr + i, x);
+      total(i, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (d[k] - (x[k] * inv) * dot) * scale;
+      store8(outr + i, o);
+    }
   }
-  dot = warp_sum_f(dot);
-  const float scale = inv * a.grad_mult;
-  for (int i = lane * 8; i < a.dim; i += 256) {
-    float x[8], d[8], o[8];
-    load8(xr + i, x);
-    load8(a.dxhat_row + base + i, d);
-    if (a.col_contrib != nullptr) {
-      float e[8];
-      load8(a.col_contrib + base + i, e);
+  if (a.dot_part != nullptr) {
+    if (lane == 0) blockdot[warp] = dot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float sum = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) d[k] += e[k];
+      for (int w = 0; w < kRowsPerBlock; ++w) sum += blockdot[w];
+      a.dot_part[static_cast<size_t>(m) * gridDim.x + blockIdx.x] = sum;
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = (d[k] - (x[k] * inv) * dot) * scale;
-    store8(outr + i, o);
   }
 }
 
 struct DtArgs {
-  const float* dt_part;
+  const float* dt_part;   // recompute mode: [3][ntiles] tile sums of G' cos
+  const float* dot_part;  // stash mode: [3][nblocks] block sums of <xhat_m, dxhat_total_m>
   const float* t3;
   const float* g3;
   float* dt3;
   int ntiles;
+  int nblocks;
   int rows_global;
+  int stash;
   float grad_mult;
 };
 
 __global__ void __launch_bounds__(1024) dt_finish_kernel(const DtArgs a) {
   __shared__ double red[32];
-  const int p = blockIdx.x;
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < a.ntiles; i += blockDim.x) acc += a.dt_part[static_cast<size_t>(p) * a.ntiles + i];
-  acc = warp_sum_d(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-    v = warp_sum_d(v);
-    if (threadIdx.x == 0) {
+  __shared__ double total[3];
+  for (int p = 0; p < 3; ++p) {
+    double acc = 0.0;
+    if (a.stash) {
+      for (int i = threadIdx.x; i < a.nblocks; i += blockDim.x) acc += a.dot_part[static_cast<size_t>(p) * a.nblocks + i];
+    } else {
+      for (int i = threadIdx.x; i < a.ntiles; i += blockDim.x) acc += a.dt_part[static_cast<size_t>(p) * a.ntiles + i];
+    }
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+      v = warp_sum_d(v);
+      if (threadIdx.x == 0) total[p] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 3) {
+    const int p = threadIdx.x;
+    double dt;
+    if (a.stash) {
+      // S_m = dt_m + dt_{(m+2)%3}  =>  dt_p = (S_p + S_{(p+1)%3} - S_{(p+2)%3}) / 2
+      dt = 0.5 * (total[p] + total[(p + 1) % 3] - total[(p + 2) % 3]);
+    } else {
       float mx = 0.f;
       for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(a.t3[r]) * a.g3[r]));
-      a.dt3[p] = static_cast<float>(v * (static_cast<double>(mx) / (static_cast<double>(kKappa) * a.rows_global)) * a.grad_mult);
+      dt = total[p] * (static_cast<double>(mx) / (static_cast<double>(kKappa) * a.rows_global));
     }
+    a.dt3[p] = static_cast<float>(dt * a.grad_mult);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stash path
+// Positive-pair logits of this rank's rows from the fp16 operands: diag_all[p][row_offset + i] = s_p <xr_i, xc_i>
+struct DiagArgs {
+  const __half* xhat[3];  // at this rank's first row
+  const float* t3;
+  float* diag_all;        // [3][rows_global]
+  int rows, dim, rows_global, row_offset;
+};
+
+__global__ void __launch_bounds__(kRowsPerBlock * 32) diag_kernel(const DiagArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kRowsPerBlock + warp;
+  if (row >= a.rows) return;
+  float dots[3] = {0.f, 0.f, 0.f};
+  for (int i = lane * 8; i < a.dim; i += 256) {
+    float x[3][8];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) load8(a.xhat[m] + static_cast<size_t>(row) * a.dim + i, x[m]);
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      float part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part = fmaf(x[p][k], x[(p + 1) % 3][k], part);
+      dots[p] += part;
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    const float d = warp_sum_f(dots[p]);
+    if (lane == 0) a.diag_all[static_cast<size_t>(p) * a.rows_global + a.row_offset + row] = expf(a.t3[p]) * d;
+  }
+}
+
+// Per-row and per-column factors of the stash -> G' conversion (see backward_scale_kernel)
+struct FactorArgs {
+  const float* t3;
+  const float* g3;
+  const float* diag_all;  // [3][rows_global]
+  const float* lse_row;   // [3][rows_local]
+  const float* lse_col;   // [3][rows_global]
+  float* fac_row;         // [3][2][rows_local]
+  float* fac_col;         // [3][2][rows_global]
+  int rows_local, rows_global, row_offset;
+};
+
+__global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs a) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int p = blockIdx.y;
+  float mx = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(a.t3[r]) * a.g3[r]));
+  const float cp = mx > 0.f ? expf(a.t3[p]) * a.g3[p] / mx : 0.f;
+  const float k8 = 8.0f * kKappa * cp;  // (kappa c_p / 2) * 16: the stash carries a 2^-4 headroom factor
+  if (i < a.rows_local) {
+    const float hd = 0.5f * a.diag_all[static_cast<size_t>(p) * a.rows_global + a.row_offset + i];
+    a.fac_row[(static_cast<size_t>(p) * 2 + 0) * a.rows_local + i] = k8 * expf(hd - a.lse_row[static_cast<size_t>(p) * a.rows_local + i]);
+    a.fac_row[(static_cast<size_t>(p) * 2 + 1) * a.rows_local + i] = expf(hd);
+  }
+  if (i < a.rows_global) {
+    const float hd = 0.5f * a.diag_all[static_cast<size_t>(p) * a.rows_global + i];
+    a.fac_col[(static_cast<size_t>(p) * 2 + 0) * a.rows_global + i] = expf(hd);
+    a.fac_col[(static_cast<size_t>(p) * 2 + 1) * a.rows_global + i] = k8 * expf(hd - a.lse_col[static_cast<size_t>(p) * a.rows_global + i]);
+  }
+}
+
+// In place on the fp16 strip: stash E~_ij = exp(L_ij - (L_ii + L_jj)/2) / 16  ->  G'_ij (without the -kappa c_p I term)
+//   G'_ij = E~_ij (R1_i C1_j + R2_i C2_j),  R1 = 8 kappa c_p exp(L_ii/2 - lse_row_i), C1 = exp(L_jj/2),
+//                                            R2 = exp(L_ii/2),                       C2 = 8 kappa c_p exp(L_jj/2 - lse_col_j)
+// HBM-bound: 2 bytes in + 2 bytes out per element; each thread keeps the factors of its 8 columns in registers and
+// walks down kScaleRows rows.
+constexpr int kScaleRows = 16;
+struct ScaleArgs {
+  __half* g;             // [3][rows_local][ld]
+  const float* fac_row;  // [3][2][rows_local]
+  const float* fac_col;  // [3][2][rows_global]
+  int rows_local, rows_global, ld;
+};
+
+__global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) {
+  const int p = blockIdx.z;
+  const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (col >= a.rows_global) return;
+  float c1[8], c2[8];
+  const float* fc = a.fac_col + static_cast<size_t>(p) * 2 * a.rows_global;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool ok = col + k < a.rows_global;
+    c1[k] = ok ? fc[col + k] : 0.f;
+    c2[k] = ok ? fc[a.rows_global + col + k] : 0.f;
+  }
+  const float* fr = a.fac_row + static_cast<size_t>(p) * 2 * a.rows_local;
+  const int row0 = blockIdx.y * kScaleRows;
+#pragma unroll 4
+  for (int r = 0; r < kScaleRows; ++r) {
+    const int row = row0 + r;
+    if (row >= a.rows_local) break;
+    const float r1 = fr[row], r2 = fr[a.rows_local + row];
+    __half* ptr = a.g + (static_cast<size_t>(p) * a.rows_local + row) * a.ld + col;
+    float v[8];
+    load8(ptr, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= fmaf(r1, c1[k], r2 * c2[k]);
+    *reinterpret_cast<uint4*>(ptr) = pack8_half(v);
   }
 }
 
@@ -343,20 +512,27 @@ int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* los
 }
 
 int launch_backward_finish(const Workspace& w, const void* const x3[3], const float* t3, const float* g3,
-                           const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, float* dt3,
-                           cudaStream_t stream) {
+                           const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, int stash,
+                           float* dt3, cudaStream_t stream) {
   FinishArgs a;
+  const size_t d = w.pb.dim;
   for (int m = 0; m < 3; ++m) {
     a.x[m] = x3[m];
     a.dx[m] = dx3[m];
+    a.xhat[m] = w.xhat[m] + static_cast<size_t>(w.pb.row_offset) * d;
   }
   a.dxhat_row = w.dxhat_row;
   a.col_contrib = col_contrib;
   a.inv_norm = w.inv_norm;
+  a.t3 = t3;
+  a.g3 = g3;
   a.rows = w.pb.rows_local;
   a.dim = w.pb.dim;
+  a.rows_global = w.pb.rows_global;
+  a.stash = stash;
   a.grad_mult = grad_mult;
   dim3 grid((a.rows + kRowsPerBlock - 1) / kRowsPerBlock, 3);
+  a.dot_part = stash ? w.dot_part : nullptr;
   const int threads = kRowsPerBlock * 32;
   if (w.pb.dtype == SCLIP_F32)
     backward_finish_kernel<float, float><<<grid, threads, 0, stream>>>(a);
@@ -366,10 +542,38 @@ int launch_backward_finish(const Workspace& w, const void* const x3[3], const fl
     backward_finish_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, threads, 0, stream>>>(a);
   SCLIP_CUDA_OK(cudaGetLastError());
   if (dt3 != nullptr) {
-    DtArgs d{w.dt_part, t3, g3, dt3, w.lay.row_tiles * w.lay.col_tiles, w.pb.rows_global, grad_mult};
-    dt_finish_kernel<<<3, 1024, 0, stream>>>(d);
+    DtArgs dd{w.dt_part, w.dot_part, t3, g3, dt3, w.lay.row_tiles * w.lay.col_tiles, static_cast<int>(grid.x),
+              w.pb.rows_global, stash, grad_mult};
+    dt_finish_kernel<<<1, 1024, 0, stream>>>(dd);
     SCLIP_CUDA_OK(cudaGetLastError());
   }
+  return SCLIP_OK;
+}
+
+int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream) {
+  DiagArgs a;
+  for (int m = 0; m < 3; ++m) a.xhat[m] = w.xhat[m] + static_cast<size_t>(w.pb.row_offset) * w.pb.dim;
+  a.t3 = t3;
+  a.diag_all = w.diag_all;
+  a.rows = w.pb.rows_local;
+  a.dim = w.pb.dim;
+  a.rows_global = w.pb.rows_global;
+  a.row_offset = w.pb.row_offset;
+  diag_kernel<<<(a.rows + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
+  FactorArgs f{t3, g3, w.diag_all, w.lse_row, w.lse_col, w.fac_row, w.fac_col,
+               w.pb.rows_local, w.pb.rows_global, w.pb.row_offset};
+  const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
+  backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  ScaleArgs a{w.g[0], w.fac_row, w.fac_col, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g};
+  dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);
+  backward_scale_kernel<<<grid, 256, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
   return SCLIP_OK;
 }
 

@@ -309,6 +309,13 @@ __device__ __forceinline__ float frag_row_sum(float (&rp)[4], int lane, int& row
 constexpr uint32_t kBarAll = 1;     // named barrier of all epilogue threads
 constexpr uint32_t kBarSlice = 2;   // + slice: the 128 threads (4 warps, one per lane quarter) of one column slice
 
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+constexpr int kSlabBytes = BM * 64 * 2;  // one 128-row x 64-column fp16 slab (16 KiB) staged for a TMA store
+
 // ============================================================================================== forward tiles
 template <int CG>
 __device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int tj_begin = 0) {
@@ -330,10 +337,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
   constexpr int NCH = CS / 32;     // 32-column chunks per warp
   constexpr uint32_t kEpiThreads = 32 * EW;
   __shared__ PipeBarriers bars;
+  constexpr int NSLAB = CS / 64;   // 64-column slabs per slice (stash stores)
   __shared__ float colacc[kAccStages][4][BN];
   __shared__ float rowacc[kAccStages][S][BM];
   __shared__ float redw[kAccStages][kMaxEpiWarps];
+  __shared__ __align__(8) float colh[kAccStages][BN];
   uint8_t* smem = aligned_dyn_smem();
+  uint8_t* staging = smem + P.stages * Geo<CG>::kStageBytes;  // stash mode: S * NSLAB = 4 slabs
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
@@ -385,6 +395,20 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       const bool edge = (m0 + BM > P.rows_local) || (n0 + BN > P.rows_global);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
 
+      // stash scaling: E~_ij = 2^(acc c - h_i - h_j), h = (L_ii / 2) log2(e) + 2, prepared while the MMAs run
+      float hr[4] = {0.f, 0.f, 0.f, 0.f};
+      if (P.stash) {
+        const float* dg = P.diag_all + static_cast<size_t>(p) * P.rows_global;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = wrow0 + 16 * (j >> 1) + 8 * (j & 1) + (lane >> 2);
+          hr[j] = row < P.rows_local ? fmaf(0.5f * kLog2e, dg[P.row_offset + row], 2.0f) : 0.f;
+        }
+        for (int cc = epi_tid; cc < BN; cc += kEpiThreads)
+          colh[acc][cc] = (n0 + cc < P.rows_global) ? fmaf(0.5f * kLog2e, dg[n0 + cc], 2.0f) : 0.f;
+        named_bar_sync(kBarAll, kEpiThreads);
+      }
+
       mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
       tc_fence_after();
       if (P.debug != 0) {  // profiling experiments: how long does the mainloop take without the epilogue?
@@ -430,7 +454,30 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       float rp[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t va[32];
       [[maybe_unused]] uint32_t vb[32];
-      auto process = [&](uint32_t (&v)[32], int ch) {
+      auto process = [&](uint32_t (&v)[32], int ch, uint8_t* stash_slab = nullptr, int hc = 0) {
+        if (stash_slab != nullptr) {
+          float cf[8];
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const float2 f = *reinterpret_cast<const float2*>(&colh[acc][col0 + ch * 32 + 8 * n + 2 * (lane & 3)]);
+            cf[2 * n] = f.x;
+            cf[2 * n + 1] = f.y;
+          }
+          // the four threads of a quad fill one 16-byte chunk of the swizzled staging slab
+#pragma unroll
+          for (int gh = 0; gh < 4; ++gh) {
+            const int r_in_tile = q * 32 + 16 * (gh >> 1) + 8 * (gh & 1) + (lane >> 2);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              const int i0 = 16 * (gh >> 1) + 4 * n + 2 * (gh & 1);
+              const float s0 = ex2_approx(fmaf(__uint_as_float(v[i0]), c, -(hr[gh] + cf[2 * n])));
+              const float s1 = ex2_approx(fmaf(__uint_as_float(v[i0 + 1]), c, -(hr[gh] + cf[2 * n + 1])));
+              const int chunk16 = hc * 4 + n;
+              const uint32_t off = r_in_tile * 128 + ((chunk16 ^ (r_in_tile & 7)) << 4) + 4 * (lane & 3);
+              *reinterpret_cast<uint32_t*>(stash_slab + off) = pack_half2(fminf(s0, 65504.f), fminf(s1, 65504.f));
+            }
+          }
+        }
         float e[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), c, -ref2));
@@ -453,7 +500,33 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
         const float csum = frag_column_sum(e, lane, col);
         colacc[acc][q][col0 + ch * 32 + col] = csum;
       };
-      if constexpr (EW == 8) {
+      if (P.stash) {
+        const int slice_tid = epi_tid & 127;
+        const CUtensorMap* map = &P.maps[P.store_map[p]];
+#pragma unroll
+        for (int sl = 0; sl < NSLAB; ++sl) {
+          uint8_t* slab = staging + (slice * NSLAB + sl) * kSlabBytes;  // one buffer per slab, reused one tile later
+          if (slice_tid == 0) {
+            if (NSLAB == 1) tma_store_wait_read<0>();
+            else tma_store_wait_read<NSLAB - 1>();
+          }
+          named_bar_sync(kBarSlice + slice, 128);
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            const int ch = sl * 2 + hc;
+            tmem_ld_block32(taddr + ch * 32, va);
+            tmem_ld_wait();
+            process(va, ch, slab, hc);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(kBarSlice + slice, 128);
+          const int gcol = n0 + col0 + sl * 64;
+          if (slice_tid == 0) {
+            if (gcol < P.rows_global) tma_store_2d(map, slab, gcol, m0);
+            tma_store_commit();
+          }
+        }
+      } else if constexpr (EW == 8) {
         // software pipeline: the TMEM load of chunk ch + 1 is in flight while chunk ch is processed
         tmem_ld_block32(taddr, va);
 #pragma unroll
@@ -495,18 +568,12 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       }
       if (epi_tid == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ref2 / kLog2e;
     }
+    if (P.stash && (epi_tid & 127) == 0) tma_store_wait_all<0>();
   }
   kernel_teardown<CG, EW>(tmem_base, warp);
 }
 
 // ============================================================================================== backward tiles
-__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-constexpr int kSlabBytes = BM * 64 * 2;  // one 128-row x 64-column fp16 slab of G' (16 KiB)
-
 template <int CG, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) backward_tiles_kernel(const __grid_constant__ BwdParams P) {
   constexpr int S = EW / 4;
@@ -861,7 +928,7 @@ int tile_smem_bytes(int cg, int stages, int slabs) {
 }
 
 int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream) {
-  const int smem = tile_smem_bytes(cg, p.stages, 0);
+  const int smem = tile_smem_bytes(cg, p.stages, p.stash ? 4 : 0);
   const int total = p.npairs * (p.nti / cg) * p.tj_count;
   if (total <= 0) return SCLIP_OK;
   SCLIP_DISPATCH(forward_tiles_kernel, smem, total, stream);

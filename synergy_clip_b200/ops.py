@@ -43,7 +43,7 @@ class TriContrastiveConfig:
     """
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
-                 overlap: bool = True, comm_sms: int = 12):
+                 overlap: bool = True, comm_sms: int = 12, stash: bool = True):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -54,6 +54,7 @@ class TriContrastiveConfig:
         self.grads_fp32 = grads_fp32
         self.overlap = overlap
         self.comm_sms = comm_sms
+        self.stash = stash  # fp16-operand mode: stash tiles in the forward instead of recomputing them in the backward
 
 
 _DEFAULT = TriContrastiveConfig()
@@ -216,9 +217,17 @@ class _CudaBackend:
     def forward_tiles(self, ws, t3):
         _lib.check(self.lib.sclip_forward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_tiles")
 
-    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi):
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False):
         _lib.check(self.lib.sclip_forward_tiles_cols(byref(ws.pb), ws.ptr, _ptr(t3), int(pair_mask), int(tile_lo),
-                                                     int(tile_hi), _stream()), "sclip_forward_tiles_cols")
+                                                     int(tile_hi), 1 if stash else 0, _stream()),
+                   "sclip_forward_tiles_cols")
+
+    def forward_diag(self, ws, t3):
+        _lib.check(self.lib.sclip_forward_diag(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_diag")
+
+    def backward_scale(self, ws, t3, g3):
+        _lib.check(self.lib.sclip_backward_scale(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
+                   "sclip_backward_scale")
 
     def backward_gemms_role(self, ws, t3, g3, role):
         _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), _stream()),
@@ -242,11 +251,11 @@ class _CudaBackend:
         _lib.check(self.lib.sclip_backward_gemms(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
                    "sclip_backward_gemms")
 
-    def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3):
+    def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3, stashed=False):
         _lib.check(
             self.lib.sclip_backward_finish(byref(ws.pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3), _ptr(g3),
                                            _ptr(col), ctypes.c_float(mult), _ptr(dimg), _ptr(dtxt), _ptr(daud),
-                                           int(out_f32), _ptr(dt3), _stream()),
+                                           int(out_f32), 1 if stashed else 0, _ptr(dt3), _stream()),
             "sclip_backward_finish")
 
 
@@ -255,15 +264,21 @@ class _CudaBackend:
 _BACKEND = _CudaBackend()
 
 
-def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) -> torch.Tensor:
+def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, keep: bool = False) -> torch.Tensor:
+    """keep: a backward will follow on this workspace.  With fp16 operands the forward then also stores the scaled
+    exponentials of every tile (the "stash") so that the backward does not recompute the similarity matrices."""
     be = _BACKEND
     pb, lay = ws.pb, ws.lay
+    stash = bool(keep) and pb.math == MATH_F16 and cfg.stash
+    ws.stashed = stash
     _mark("begin")
     be.prologue(ws, img, txt, aud)
+    if stash:
+        be.forward_diag(ws, t3)
     _mark("prologue")
     loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
     if pb.world == 1:
-        be.forward_tiles(ws, t3)
+        be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
         _mark("forward_tiles")
         be.forward_reduce(ws)
         be.forward_loss(ws, None, loss3)
@@ -281,12 +296,19 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) 
         for buf in bufs:
             dist.all_gather_into_tensor(buf[m].view(-1), buf[m, off:off + bl].reshape(-1), group=pg)
 
+    def gather_diag():  # positive-pair logits of every rank's rows (column scaling of the stash)
+        if stash:
+            dg = ws.view(lay.diag_all, (3, bg), torch.float32)
+            for p in range(3):
+                dist.all_gather_into_tensor(dg[p], dg[p, off:off + bl], group=pg)
+
     overlap = cfg.overlap and img.is_cuda and bl % 256 == 0
     if not overlap:
+        gather_diag()
         for m in range(3):
             gather(m)
         _mark("all_gather")
-        be.forward_tiles(ws, t3)
+        be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
     else:
         # Pair p needs the gathered column modality (p + 1) % 3.  Gather txt, aud, img in that order on the side stream;
         # meanwhile run the tiles whose columns are this rank's own rows, then pair IT, TA, AI as their operands land.
@@ -297,6 +319,7 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) 
         landed = []
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
+            gather_diag()
             for m in (1, 2, 0):
                 gather(m)
                 ev = torch.cuda.Event()
@@ -305,13 +328,13 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig) 
         lo, hi = off // 256, (off + bl) // 256
         prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
         try:
-            be.forward_tiles_cols(ws, t3, 7, lo, hi)
+            be.forward_tiles_cols(ws, t3, 7, lo, hi, stash)
             for p, ev in enumerate(landed):
                 cur.wait_event(ev)
                 if p == 2:
                     be.set_max_sms(prev)  # nothing left in flight: use every SM again
-                be.forward_tiles_cols(ws, t3, 1 << p, 0, lo)
-                be.forward_tiles_cols(ws, t3, 1 << p, hi, lay.col_tiles)
+                be.forward_tiles_cols(ws, t3, 1 << p, 0, lo, stash)
+                be.forward_tiles_cols(ws, t3, 1 << p, hi, lay.col_tiles, stash)
         finally:
             be.set_max_sms(prev)
     _mark("forward_tiles")
@@ -333,8 +356,13 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     gdtype = torch.float32 if out_f32 else img.dtype
     dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
     dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
+    stashed = bool(getattr(ws, "stashed", False))
+    ws.stashed = False  # the stash is converted in place: it can be consumed once
     _mark("backward_begin")
-    be.backward_tiles(ws, t3, g3)
+    if stashed:
+        be.backward_scale(ws, t3, g3)
+    else:
+        be.backward_tiles(ws, t3, g3)
     _mark("backward_tiles")
     col = None
     mult = 1.0
@@ -378,7 +406,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             _mark("backward_gemms")
         if cfg.grad_scale == "ddp":
             mult = float(pb.world)
-    be.backward_finish(ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3)
+    be.backward_finish(ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3, stashed)
     _mark("backward_finish")
     if pb.world > 1 and cfg.grad_scale == "sum":
         import torch.distributed as dist
@@ -394,16 +422,20 @@ class _TriContrastive(torch.autograd.Function):
         pb, _, _ = _make_problem(img, cfg)
         ws = _POOL.acquire(pb, img.device)
         lease = _Lease(ws)
-        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg)
+        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         ctx.save_for_backward(img, txt, aud, t3)
         ctx.lease = lease
         ctx.cfg = cfg
+        ctx.stashed = ws.stashed
         return loss3
 
     @staticmethod
     def backward(ctx, g3):
         img, txt, aud, t3 = ctx.saved_tensors
         ws = ctx.lease.ws
+        if ctx.stashed and not ws.stashed:
+            raise _lib.SclipError("the contrastive objective was already back-propagated once: its stashed tiles are "
+                                  "converted in place and cannot serve a second backward (retain_graph)")
         g3 = g3.to(torch.float32).contiguous()
         dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, ctx.cfg)
         if not ctx.cfg.grads_fp32:
@@ -439,7 +471,7 @@ def forward_backward_raw(img, txt, aud, t3, g3, config: Optional[TriContrastiveC
     pb, _, _ = _make_problem(img, cfg)
     ws = _POOL.acquire(pb, img.device)
     try:
-        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg)
+        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, cfg)
     finally:
         _POOL.release(ws)

@@ -67,7 +67,14 @@ class EmulatedBackend:
     def forward_tiles(self, ws, t3):
         self.forward_tiles_cols(ws, t3, 7, 0, ws.lay.col_tiles)
 
-    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi):
+    def forward_diag(self, ws, t3):
+        bl, bg, d, off = self._dims(ws)
+        xh = ws.view(ws.lay.xhat, (3, bg, d), torch.float16).double()
+        dg = ws.view(ws.lay.diag_all, (3, bg), torch.float32)
+        for p, (r, c) in enumerate(PAIRS):
+            dg[p, off:off + bl] = (math.exp(float(t3[p])) * (xh[r, off:off + bl] * xh[c, off:off + bl]).sum(-1)).float()
+
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False):
         """Column tiles [tile_lo, tile_hi) of the pairs in pair_mask; row partials land in slot `tile_lo`."""
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
@@ -92,6 +99,10 @@ class EmulatedBackend:
             col_part[p, 0, c0:c1] = e.sum(0).float()
             if c0 <= off < c1:
                 diag[p] = logits[torch.arange(bl), off + torch.arange(bl)].float()
+            if stash:
+                dg = ws.view(lay.diag_all, (3, bg), torch.float32).double()[p]
+                st = torch.exp(logits[:, c0:c1] - 0.5 * (dg[off:off + bl, None] + dg[None, c0:c1])) / 16.0
+                ws.view(lay.grad_tiles, (3, bl, lay.ld_g), torch.float16)[p, :, c0:c1] = st.clamp(max=65504.0).half()
 
     def forward_reduce(self, ws):
         bl, bg, d, off = self._dims(ws)
@@ -149,6 +160,21 @@ class EmulatedBackend:
             if self._x3(ws):
                 ws.view(lay.grad_tiles_lo, (3, bl, lay.ld_g), torch.float16)[p, :, :bg] = (gp - h.double()).half()
 
+    def backward_scale(self, ws, t3, g3):
+        bl, bg, d, off = self._dims(ws)
+        lay = ws.lay
+        _, cps = self._coeffs(t3, g3)
+        g = ws.view(lay.grad_tiles, (3, bl, lay.ld_g), torch.float16)
+        dg = ws.view(lay.diag_all, (3, bg), torch.float32).double()
+        lse_row = ws.view(lay.lse_row, (3, bl), torch.float32).double()
+        lse_col = ws.view(lay.lse_col, (3, bg), torch.float32).double()
+        for p in range(3):
+            k8 = 8.0 * KAPPA * cps[p]
+            hr, hc = 0.5 * dg[p, off:off + bl], 0.5 * dg[p]
+            fac = (k8 * torch.exp(hr - lse_row[p]))[:, None] * torch.exp(hc)[None, :] + \
+                torch.exp(hr)[:, None] * (k8 * torch.exp(hc - lse_col[p]))[None, :]
+            g[p, :, :bg] = (g[p, :, :bg].double() * fac).half()
+
     def _gprime(self, ws):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
@@ -183,16 +209,28 @@ class EmulatedBackend:
                 if role in (0, 1):
                     ws.view(lay.dxhat_col, (3, bg, d), torch.float32)[m] = (alpha * col_role).float()
 
-    def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3):
+    def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3, stashed=False):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
         inv = ws.view(lay.inv_norm, (3, bl), torch.float32).double()
         row_out = ws.view(lay.dxhat_row, (3, bl, d), torch.float32).double()
+        xh16 = ws.view(lay.xhat, (3, bg, d), torch.float16).double()[:, off:off + bl]
+        dots = []
         for m, (x, out) in enumerate(zip((img, txt, aud), (dimg, dtxt, daud))):
             dd = row_out[m] + (col[m].double() if col is not None else 0.0)
+            if stashed:  # the "- kappa c_p I" term of G' that the scaled stash does not carry
+                m1, m2 = (m + 1) % 3, (m + 2) % 3
+                k1 = math.exp(float(t3[m])) * float(g3[m]) / bg
+                k2 = math.exp(float(t3[m2])) * float(g3[m2]) / bg
+                dd = dd - k1 * xh16[m1] - k2 * xh16[m2]
             xh = x.double() * inv[m][:, None]
+            dots.append(float((xh * dd).sum()))
             dx = (dd - xh * (xh * dd).sum(-1, keepdim=True)) * inv[m][:, None] * mult
             out.copy_(dx.to(out.dtype))
-        mx, _ = self._coeffs(t3, g3)
-        dt_part = ws.view(lay.dt_part, (3, lay.row_tiles * lay.col_tiles), torch.float32).double()
-        dt3.copy_((dt_part.sum(1) * mx / (KAPPA * bg) * mult).float())
+        if stashed:
+            dt = [0.5 * (dots[p] + dots[(p + 1) % 3] - dots[(p + 2) % 3]) * mult for p in range(3)]
+            dt3.copy_(torch.tensor(dt, dtype=torch.float32))
+        else:
+            mx, _ = self._coeffs(t3, g3)
+            dt_part = ws.view(lay.dt_part, (3, lay.row_tiles * lay.col_tiles), torch.float32).double()
+            dt3.copy_((dt_part.sum(1) * mx / (KAPPA * bg) * mult).float())

@@ -43,7 +43,7 @@ class TriContrastiveConfig:
     """
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
-                 overlap: bool = True, comm_sms: int = 12, stash: bool = True):
+                 overlap: bool = True, comm_sms: int = 12, stash="auto"):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -54,7 +54,12 @@ class TriContrastiveConfig:
         self.grads_fp32 = grads_fp32
         self.overlap = overlap
         self.comm_sms = comm_sms
-        self.stash = stash  # fp16-operand mode: stash tiles in the forward instead of recomputing them in the backward
+        # fp16-operand mode only: store the scaled exponentials of every tile in the forward ("stash") and convert them
+        # in place in the backward (4 bytes of HBM traffic per logit) instead of recomputing the similarity matrices
+        # (2 D flop per logit).  "auto": stash when D >= 640 -- measured crossover on B200 (D = 512: recompute wins).
+        if stash not in ("auto", True, False):
+            raise ValueError(f"stash={stash!r}")
+        self.stash = stash
 
 
 _DEFAULT = TriContrastiveConfig()
@@ -269,7 +274,7 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
     exponentials of every tile (the "stash") so that the backward does not recompute the similarity matrices."""
     be = _BACKEND
     pb, lay = ws.pb, ws.lay
-    stash = bool(keep) and pb.math == MATH_F16 and cfg.stash
+    stash = bool(keep) and pb.math == MATH_F16 and (pb.dim >= 640 if cfg.stash == "auto" else bool(cfg.stash))
     ws.stashed = stash
     _mark("begin")
     be.prologue(ws, img, txt, aud)

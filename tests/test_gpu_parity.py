@@ -47,6 +47,32 @@ def test_golden_fp32_split_operands(name):
     assert max(errs.values()) < TOL_F32, errs
 
 
+@pytest.mark.parametrize("b,d,t", [(700, 512, 2.6592), (300, 768, math.log(100.0))])
+def test_stash_and_recompute_backwards_agree(b, d, t):
+    """fp16-operand mode has two backward paths (stash in the forward vs recompute the similarities): both must meet
+    the oracle and agree with each other far inside the tolerance, on the unshifted (s < 64) and the shifted path."""
+    from synergy_clip_b200 import ops
+
+    embs = [closed_form.round_to_bf16(e) for e in closed_form.synthetic_embeddings(b, d, 31, 0.15)]
+    t3, g3 = (t, t, t), (0.25, 0.5, 0.125)
+    want = closed_form.tri_contrastive(*embs, t3, g3)
+    ten = [torch.from_numpy(e).cuda().bfloat16() for e in embs]
+    t3d = torch.tensor(t3, dtype=torch.float32, device="cuda")
+    g3d = torch.tensor(g3, dtype=torch.float32, device="cuda")
+    res = {}
+    for stash in (True, False):
+        cfg = ops.TriContrastiveConfig(math="f16", grads_fp32=True, stash=stash)
+        res[stash] = ops.forward_backward_raw(*ten, t3d, g3d, cfg)
+        torch.cuda.synchronize()
+        loss3, dimg, dtxt, daud, dt3 = res[stash]
+        assert np.max(np.abs(loss3.cpu().numpy() - want["loss"]) / want["loss"]) < TOL_F16
+        for got, key in ((dimg, "dimg"), (dtxt, "dtxt"), (daud, "daud")):
+            assert golden_util.rel(got.cpu().numpy(), want[key]) < TOL_F16, (stash, key)
+        assert np.max(np.abs(dt3.cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"])) < TOL_F16
+    assert torch.equal(res[True][0], res[False][0])  # identical forward statistics
+    assert golden_util.rel(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) < 5e-4
+
+
 def test_autograd_matches_oracle_and_respects_weights():
     from synergy_clip_b200 import fused_tri_contrastive
 

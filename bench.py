@@ -257,6 +257,8 @@ def main():
 
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
+        # the collectives run next to persistent tile kernels that leave them 20 SMs (TriContrastiveConfig.comm_sms)
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     peaks = load_peaks()

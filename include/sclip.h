@@ -88,6 +88,7 @@ typedef struct sclip_layout {
   uint64_t dxhat_row;     /* [3][rows_local][dim] fp32 d/dxhat from the row role (+ column role if world==1) */
   uint64_t dxhat_col;     /* [3][rows_global][dim] fp32 column-role partial sums (world > 1 only)
                              [exchange: reduce-scatter sum over ranks]                                        */
+  uint64_t col_contrib;   /* [3][rows_local][dim] fp32 landing buffer of that reduce-scatter (world > 1 only)            */
   uint64_t diag_all;      /* [3][rows_global] fp32 positive-pair logits of ALL rows (stash scaling); sclip_forward_diag
                              writes this rank's rows [exchange: all-gather when world > 1]                     */
   uint64_t fac_row;       /* [3][2][rows_local] fp32 row factors of the stash -> G' conversion                 */

@@ -32,7 +32,7 @@ class Layout(Structure):
     _fields_ = [(name, c_uint64) for name in (
         "total_bytes", "xhat", "xhat_lo", "inv_norm", "row_part", "col_part", "tile_ref", "diag", "lse_row",
         "lse_col_local", "lse_col", "row_inv", "col_sum_local", "col_inv", "loss_part", "grad_tiles", "grad_tiles_lo", "dt_part", "dxhat_row", "dxhat_col",
-        "diag_all", "fac_row", "fac_col", "dot_part", "status")] + [("row_tiles", c_int32), ("col_tiles", c_int32), ("ld_g", c_int32), ("reserved", c_int32)]
+        "col_contrib", "diag_all", "fac_row", "fac_col", "dot_part", "status")] + [("row_tiles", c_int32), ("col_tiles", c_int32), ("ld_g", c_int32), ("reserved", c_int32)]
 
 
 class SclipError(RuntimeError):

@@ -124,6 +124,7 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->dt_part = take(3 * nti * ntj * 4);
   lay->dxhat_row = take(3 * bl * d * 4);
   lay->dxhat_col = pb->world > 1 ? take(3 * bg * d * 4) : lay->dxhat_row;
+  lay->col_contrib = pb->world > 1 ? take(3 * bl * d * 4) : lay->dxhat_row;
   lay->diag_all = take(3 * bg * 4);
   lay->fac_row = take(3 * 2 * bl * 4);
   lay->fac_col = take(3 * 2 * bg * 4);

@@ -43,7 +43,7 @@ class TriContrastiveConfig:
     """
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
-                 overlap: bool = True, comm_sms: int = 12, stash="auto"):
+                 overlap: bool = True, comm_sms: int = 20, stash="auto"):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -74,6 +74,31 @@ def _mark(name: str) -> None:
 
 
 _COMM_STREAMS = {}
+
+
+def _all_gather(pieces, group, coalesce):
+    """pieces: [(output, this rank's input)]; one NCCL group launch when `coalesce`."""
+    import torch.distributed as dist
+
+    if coalesce and len(pieces) > 1:
+        with dist._coalescing_manager(group=group):
+            for out, inp in pieces:
+                dist.all_gather_into_tensor(out, inp, group=group)
+    else:
+        for out, inp in pieces:
+            dist.all_gather_into_tensor(out, inp, group=group)
+
+
+def _reduce_scatter(pieces, group, coalesce):
+    import torch.distributed as dist
+
+    if coalesce and len(pieces) > 1:
+        with dist._coalescing_manager(group=group):
+            for out, inp in pieces:
+                dist.reduce_scatter_tensor(out, inp, group=group)
+    else:
+        for out, inp in pieces:
+            dist.reduce_scatter_tensor(out, inp, group=group)
 
 
 def _comm_stream(device: torch.device) -> "torch.cuda.Stream":
@@ -293,55 +318,45 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
 
     pg = cfg.process_group
     bl, bg, d, off = pb.rows_local, pb.rows_global, pb.dim, pb.row_offset
+    # all-gather of the normalised row shards (each modality is column-side in one pair) and, for the stash, of the
+    # positive-pair logits: one coalesced NCCL launch
+    pieces = []
     bufs = [ws.view(lay.xhat, (3, bg, d), torch.float16)]
     if pb.math == MATH_F16X3:
         bufs.append(ws.view(lay.xhat_lo, (3, bg, d), torch.float16))
-
-    def gather(m):  # all-gather of the normalised row shards of modality m
-        for buf in bufs:
-            dist.all_gather_into_tensor(buf[m].view(-1), buf[m, off:off + bl].reshape(-1), group=pg)
-
-    def gather_diag():  # positive-pair logits of every rank's rows (column scaling of the stash)
-        if stash:
-            dg = ws.view(lay.diag_all, (3, bg), torch.float32)
-            for p in range(3):
-                dist.all_gather_into_tensor(dg[p], dg[p, off:off + bl], group=pg)
+    for buf in bufs:
+        for m in range(3):
+            pieces.append((buf[m].view(-1), buf[m, off:off + bl].reshape(-1)))
+    if stash:
+        dg = ws.view(lay.diag_all, (3, bg), torch.float32)
+        for p in range(3):
+            pieces.append((dg[p].view(torch.float16), dg[p, off:off + bl].view(torch.float16)))
 
     overlap = cfg.overlap and img.is_cuda and bl % 256 == 0
     if not overlap:
-        gather_diag()
-        for m in range(3):
-            gather(m)
+        _all_gather(pieces, pg, img.is_cuda)
         _mark("all_gather")
         be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
     else:
-        # Pair p needs the gathered column modality (p + 1) % 3.  Gather txt, aud, img in that order on the side stream;
-        # meanwhile run the tiles whose columns are this rank's own rows, then pair IT, TA, AI as their operands land.
+        # the gather runs on the side stream under the tiles whose columns are this rank's own rows
         cur = torch.cuda.current_stream()
         comm = _comm_stream(img.device)
         ready = torch.cuda.Event()
         ready.record(cur)
-        landed = []
+        landed = torch.cuda.Event()
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
-            gather_diag()
-            for m in (1, 2, 0):
-                gather(m)
-                ev = torch.cuda.Event()
-                ev.record(comm)
-                landed.append(ev)
+            _all_gather(pieces, pg, True)
+            landed.record(comm)
         lo, hi = off // 256, (off + bl) // 256
         prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
         try:
             be.forward_tiles_cols(ws, t3, 7, lo, hi, stash)
-            for p, ev in enumerate(landed):
-                cur.wait_event(ev)
-                if p == 2:
-                    be.set_max_sms(prev)  # nothing left in flight: use every SM again
-                be.forward_tiles_cols(ws, t3, 1 << p, 0, lo, stash)
-                be.forward_tiles_cols(ws, t3, 1 << p, hi, lay.col_tiles, stash)
         finally:
             be.set_max_sms(prev)
+        cur.wait_event(landed)
+        be.forward_tiles_cols(ws, t3, 7, 0, lo, stash)
+        be.forward_tiles_cols(ws, t3, 7, hi, lay.col_tiles, stash)
     _mark("forward_tiles")
     be.forward_reduce(ws)
     # column statistics: every rank holds the log-sum-exp over its own rows; merge them over ranks
@@ -379,11 +394,10 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
 
         bl, bg, d = pb.rows_local, pb.rows_global, pb.dim
         part = ws.view(lay.dxhat_col, (3, bg, d), torch.float32)
-        col = torch.empty((3, bl, d), dtype=torch.float32, device=img.device)
+        col = ws.view(lay.col_contrib, (3, bl, d), torch.float32)
 
-        def scatter():  # reduce-scatter of the column-role partial gradients
-            for m in range(3):
-                dist.reduce_scatter_tensor(col[m].view(-1), part[m].view(-1), group=cfg.process_group)
+        def scatter():  # reduce-scatter of the column-role partial gradients: one coalesced NCCL launch
+            _reduce_scatter([(col[m].view(-1), part[m].view(-1)) for m in range(3)], cfg.process_group, img.is_cuda)
 
         if not (cfg.overlap and img.is_cuda):
             be.backward_gemms(ws, t3, g3)
@@ -396,7 +410,6 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             be.backward_gemms_role(ws, t3, g3, 1)  # column role first ...
             done = torch.cuda.Event()
             done.record(cur)
-            col.record_stream(comm)
             with torch.cuda.stream(comm):
                 comm.wait_event(done)
                 scatter()                            # ... its reduce-scatter runs under the row-role GEMMs

@@ -91,8 +91,8 @@ typedef struct sclip_layout {
   uint64_t col_contrib;   /* [3][rows_local][dim] fp32 landing buffer of that reduce-scatter (world > 1 only)            */
   uint64_t diag_all;      /* [3][rows_global] fp32 positive-pair logits of ALL rows (stash scaling); sclip_forward_diag
                              writes this rank's rows [exchange: all-gather when world > 1]                     */
-  uint64_t fac_row;       /* [3][2][rows_local] fp32 row factors of the stash -> G' conversion                 */
-  uint64_t fac_col;       /* [3][2][rows_global] fp32 column factors                                           */
+  uint64_t fac_row;       /* [3][2][rows_local rounded up to 64] fp32 row factors of the stash -> G' conversion */
+  uint64_t fac_col;       /* [3][2][rows_global rounded up to 64] fp32 column factors                           */
   uint64_t dot_part;      /* [3][ceil(rows_local/8)] fp32 partial sums of <xhat, dxhat> (stash mode dlogit_scale) */
   uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed) */
   int32_t row_tiles;      /* ceil(rows_local / 128)   */
@@ -156,18 +156,25 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
  * applied by sclip_backward_finish with SCLIP_BWD_STASHED).  HBM-bound elementwise pass. */
 int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
+/* Only the factor vectors R1, R2, C1, C2 of that conversion; the gradient GEMMs then convert the stashed tiles in
+ * shared memory on their way to the tensor cores (sclip_backward_gemms_role with SCLIP_BWD_STASHED) and the HBM pass
+ * of sclip_backward_scale disappears. */
+int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
+
 /* dxhat_row[m] = G'_{rowpair(m)} . xhat_{col modality}   (rows_local x dim, complete)
  * dxhat_col[m] = G'_{colpair(m)}^T . xhat_{row modality} (rows_global x dim partial sums; world == 1: added
  *                into dxhat_row by the same accumulator instead). */
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
 /* Same, one role at a time (world > 1): SCLIP_ROLE_COLUMN writes only dxhat_col (so its reduce-scatter can start),
- * SCLIP_ROLE_ROW only dxhat_row; SCLIP_ROLE_BOTH == sclip_backward_gemms. */
+ * SCLIP_ROLE_ROW only dxhat_row; SCLIP_ROLE_BOTH == sclip_backward_gemms.
+ * flags & SCLIP_BWD_STASHED: grad_tiles still holds the raw stash of the forward (sclip_backward_factors has run,
+ * sclip_backward_scale has not): every A tile is multiplied by (R1_i C1_j + R2_i C2_j) in shared memory. */
 #define SCLIP_ROLE_BOTH 0
 #define SCLIP_ROLE_COLUMN 1
 #define SCLIP_ROLE_ROW 2
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
-                              void* stream);
+                              int flags, void* stream);
 
 /* Process-wide launch option: the persistent tile kernels use at most max_sms SMs (0 = all), leaving the rest to
  * concurrently running communication kernels.  Returns the previous value. */

@@ -126,8 +126,8 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->dxhat_col = pb->world > 1 ? take(3 * bg * d * 4) : lay->dxhat_row;
   lay->col_contrib = pb->world > 1 ? take(3 * bl * d * 4) : lay->dxhat_row;
   lay->diag_all = take(3 * bg * 4);
-  lay->fac_row = take(3 * 2 * bl * 4);
-  lay->fac_col = take(3 * 2 * bg * 4);
+  lay->fac_row = take(3 * 2 * align_up(bl, 64) * 4);
+  lay->fac_col = take(3 * 2 * align_up(bg, 64) * 4);
   lay->dot_part = take(3 * ((bl + 7) / 8) * 4);
   lay->status = take(4 * 4);
   lay->total_bytes = off;
@@ -285,7 +285,7 @@ struct MapTable {
   }
 };
 
-Segment seg(int a, int b, int a_mn, int b_mn, int num_kb) { return Segment{a, b, a_mn, b_mn, num_kb}; }
+Segment seg(int a, int b, int a_mn, int b_mn, int num_kb) { return Segment{a, b, a_mn, b_mn, num_kb, 0, 0, 0, 0, 0}; }
 
 // similarity job of pair p (forward and the backward recompute)
 void similarity_job(const Workspace& w, MapTable& t, int p, Job* job) {
@@ -361,7 +361,18 @@ int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3
     set_error("sclip_backward_scale needs t3, g3 and a SCLIP_MATH_F16 problem");
     return SCLIP_ERR_ARGUMENT;
   }
-  return launch_backward_scale(w, t3, g3, static_cast<cudaStream_t>(stream));
+  return launch_backward_scale(w, t3, g3, false, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr || g3 == nullptr || w.pb.math != SCLIP_MATH_F16) {
+    set_error("sclip_backward_factors needs t3, g3 and a SCLIP_MATH_F16 problem");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_backward_scale(w, t3, g3, true, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
@@ -466,11 +477,11 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
 }
 
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
-  return sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, stream);
+  return sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, stream);
 }
 
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
-                              void* stream) {
+                              int flags, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -503,6 +514,26 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
     if (do_col) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
   }
   int nj = 0, tiles = 0;
+  const bool convert = (flags & SCLIP_BWD_STASHED) != 0;
+  if (convert && x3) {
+    set_error("SCLIP_BWD_STASHED is only defined for SCLIP_MATH_F16");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  p.fac = w.fac_row;
+  const int ld_row = static_cast<int>(align_up(bl, 64)), ld_col = static_cast<int>(align_up(bg, 64));
+  const int col_base = static_cast<int>(w.fac_col - w.fac_row);  // float offset of fac_col from fac_row
+  auto conv = [&](Segment sgm, int pair, bool row_role) {
+    if (!convert) return sgm;
+    const int r1 = (pair * 2 + 0) * ld_row, r2 = (pair * 2 + 1) * ld_row;
+    const int c1 = col_base + (pair * 2 + 0) * ld_col, c2 = col_base + (pair * 2 + 1) * ld_col;
+    sgm.transform = 1;
+    if (row_role) {  // A = stash (m = local row i, k = global column j): F = R1_i C1_j + R2_i C2_j
+      sgm.um_off = r1; sgm.um2_off = r2; sgm.wk_off = c1; sgm.wk2_off = c2;
+    } else {         // A = stash^T (m = global column j, k = local row i)
+      sgm.um_off = c1; sgm.um2_off = c2; sgm.wk_off = r1; sgm.wk2_off = r2;
+    }
+    return sgm;
+  };
   auto add_role = [&](Job& job, int m, bool row_role) {
     if (row_role) {  // G'_{pair m} (rows_local x rows_global, K-major) . xhat_{col modality} (k = global row)
       const int pr = modality_row_pair(m), cm = pair_col_modality(pr);
@@ -510,14 +541,14 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
         job.seg[job.nseg++] = seg(tab.use(kGloK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
         job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
       }
-      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
+      job.seg[job.nseg++] = conv(seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g), pr, true);
     } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
       const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
       if (x3) {
         job.seg[job.nseg++] = seg(tab.use(kGloMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
         job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXloLocMN + rm), 1, 1, kb_l);
       }
-      job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
+      job.seg[job.nseg++] = conv(seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l), pc, false);
     }
   };
   for (int m = 0; m < 3 && do_row; ++m) {
@@ -610,9 +641,9 @@ int sclip_backward(const sclip_problem* problem, void* ws, const void* img, cons
     return SCLIP_ERR_ARGUMENT;
   }
   const bool stashed = ws != nullptr && g_stashed_ws == ws;
-  int rc = stashed ? sclip_backward_scale(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
-  if (stashed) g_stashed_ws = nullptr;  // the stash is consumed in place
-  if (!rc) rc = sclip_backward_gemms(problem, ws, t3, g3, stream);
+  int rc = stashed ? sclip_backward_factors(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
+  if (!rc)
+    rc = sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, stashed ? SCLIP_BWD_STASHED : 0, stream);
   if (!rc)
     rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32,
                                stashed ? SCLIP_BWD_STASHED : 0, dt3, stream);
@@ -633,7 +664,7 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
     rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN / cta_group());
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK)};
+  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK), 0, 0, 0, 0, 0};
   p.jobs[0].nseg = 1;
   p.jobs[0].ksplits = 1;
   p.jobs[0].m_tiles = ceil_div(m, BM * cta_group());

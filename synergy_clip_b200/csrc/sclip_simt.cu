@@ -403,9 +403,10 @@ struct FactorArgs {
   const float* diag_all;  // [3][rows_global]
   const float* lse_row;   // [3][rows_local]
   const float* lse_col;   // [3][rows_global]
-  float* fac_row;         // [3][2][rows_local]
-  float* fac_col;         // [3][2][rows_global]
+  float* fac_row;         // [3][2][ld_row]   (ld = rows rounded up to 64, tail zeroed)
+  float* fac_col;         // [3][2][ld_col]
   int rows_local, rows_global, row_offset;
+  int ld_row, ld_col;
 };
 
 __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs a) {
@@ -416,15 +417,25 @@ __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs 
   for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(a.t3[r]) * a.g3[r]));
   const float cp = mx > 0.f ? expf(a.t3[p]) * a.g3[p] / mx : 0.f;
   const float k8 = 8.0f * kKappa * cp;  // (kappa c_p / 2) * 16: the stash carries a 2^-4 headroom factor
-  if (i < a.rows_local) {
-    const float hd = 0.5f * a.diag_all[static_cast<size_t>(p) * a.rows_global + a.row_offset + i];
-    a.fac_row[(static_cast<size_t>(p) * 2 + 0) * a.rows_local + i] = k8 * expf(hd - a.lse_row[static_cast<size_t>(p) * a.rows_local + i]);
-    a.fac_row[(static_cast<size_t>(p) * 2 + 1) * a.rows_local + i] = expf(hd);
+  if (i < a.ld_row) {
+    float r1 = 0.f, r2 = 0.f;
+    if (i < a.rows_local) {
+      const float hd = 0.5f * a.diag_all[static_cast<size_t>(p) * a.rows_global + a.row_offset + i];
+      r1 = k8 * expf(hd - a.lse_row[static_cast<size_t>(p) * a.rows_local + i]);
+      r2 = expf(hd);
+    }
+    a.fac_row[(static_cast<size_t>(p) * 2 + 0) * a.ld_row + i] = r1;
+    a.fac_row[(static_cast<size_t>(p) * 2 + 1) * a.ld_row + i] = r2;
   }
-  if (i < a.rows_global) {
-    const float hd = 0.5f * a.diag_all[static_cast<size_t>(p) * a.rows_global + i];
-    a.fac_col[(static_cast<size_t>(p) * 2 + 0) * a.rows_global + i] = expf(hd);
-    a.fac_col[(static_cast<size_t>(p) * 2 + 1) * a.rows_global + i] = k8 * expf(hd - a.lse_col[static_cast<size_t>(p) * a.rows_global + i]);
+  if (i < a.ld_col) {
+    float c1 = 0.f, c2 = 0.f;
+    if (i < a.rows_global) {
+      const float hd = 0.5f * a.diag_all[static_cast<size_t>(p) * a.rows_global + i];
+      c1 = expf(hd);
+      c2 = k8 * expf(hd - a.lse_col[static_cast<size_t>(p) * a.rows_global + i]);
+    }
+    a.fac_col[(static_cast<size_t>(p) * 2 + 0) * a.ld_col + i] = c1;
+    a.fac_col[(static_cast<size_t>(p) * 2 + 1) * a.ld_col + i] = c2;
   }
 }
 
@@ -436,9 +447,10 @@ __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs 
 constexpr int kScaleRows = 16;
 struct ScaleArgs {
   __half* g;             // [3][rows_local][ld]
-  const float* fac_row;  // [3][2][rows_local]
-  const float* fac_col;  // [3][2][rows_global]
+  const float* fac_row;  // [3][2][ld_row]
+  const float* fac_col;  // [3][2][ld_col]
   int rows_local, rows_global, ld;
+  int ld_row, ld_col;
 };
 
 __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) {
@@ -446,20 +458,20 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
   const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= a.rows_global) return;
   float c1[8], c2[8];
-  const float* fc = a.fac_col + static_cast<size_t>(p) * 2 * a.rows_global;
+  const float* fc = a.fac_col + static_cast<size_t>(p) * 2 * a.ld_col;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const bool ok = col + k < a.rows_global;
     c1[k] = ok ? fc[col + k] : 0.f;
-    c2[k] = ok ? fc[a.rows_global + col + k] : 0.f;
+    c2[k] = ok ? fc[a.ld_col + col + k] : 0.f;
   }
-  const float* fr = a.fac_row + static_cast<size_t>(p) * 2 * a.rows_local;
+  const float* fr = a.fac_row + static_cast<size_t>(p) * 2 * a.ld_row;
   const int row0 = blockIdx.y * kScaleRows;
 #pragma unroll 4
   for (int r = 0; r < kScaleRows; ++r) {
     const int row = row0 + r;
     if (row >= a.rows_local) break;
-    const float r1 = fr[row], r2 = fr[a.rows_local + row];
+    const float r1 = fr[row], r2 = fr[a.ld_row + row];
     __half* ptr = a.g + (static_cast<size_t>(p) * a.rows_local + row) * a.ld + col;
     float v[8];
     load8(ptr, v);
@@ -564,13 +576,15 @@ int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream) {
   return SCLIP_OK;
 }
 
-int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
+int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, bool factors_only, cudaStream_t stream) {
+  const int ld_row = (w.pb.rows_local + 63) / 64 * 64, ld_col = (w.pb.rows_global + 63) / 64 * 64;
   FactorArgs f{t3, g3, w.diag_all, w.lse_row, w.lse_col, w.fac_row, w.fac_col,
-               w.pb.rows_local, w.pb.rows_global, w.pb.row_offset};
-  const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
+               w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, ld_row, ld_col};
+  const int n = ld_row > ld_col ? ld_row : ld_col;
   backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
   SCLIP_CUDA_OK(cudaGetLastError());
-  ScaleArgs a{w.g[0], w.fac_row, w.fac_col, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g};
+  if (factors_only) return SCLIP_OK;
+  ScaleArgs a{w.g[0], w.fac_row, w.fac_col, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col};
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);
   backward_scale_kernel<<<grid, 256, 0, stream>>>(a);
   SCLIP_CUDA_OK(cudaGetLastError());

@@ -43,7 +43,7 @@ class TriContrastiveConfig:
     """
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
-                 overlap: bool = True, comm_sms: int = 20, stash="auto"):
+                 overlap: bool = True, comm_sms: int = 20, stash="auto", fuse_scale: bool = True):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -60,6 +60,9 @@ class TriContrastiveConfig:
         if stash not in ("auto", True, False):
             raise ValueError(f"stash={stash!r}")
         self.stash = stash
+        # stash mode: apply the stash -> G' factors to the A tiles in shared memory inside the gradient GEMMs (True) or
+        # in a separate in-place HBM pass (False)
+        self.fuse_scale = fuse_scale
 
 
 _DEFAULT = TriContrastiveConfig()
@@ -259,9 +262,13 @@ class _CudaBackend:
         _lib.check(self.lib.sclip_backward_scale(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
                    "sclip_backward_scale")
 
-    def backward_gemms_role(self, ws, t3, g3, role):
-        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), _stream()),
-                   "sclip_backward_gemms_role")
+    def backward_gemms_role(self, ws, t3, g3, role, convert=False):
+        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role),
+                                                      1 if convert else 0, _stream()), "sclip_backward_gemms_role")
+
+    def backward_factors(self, ws, t3, g3):
+        _lib.check(self.lib.sclip_backward_factors(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
+                   "sclip_backward_factors")
 
     def set_max_sms(self, n):
         return self.lib.sclip_set_max_sms(int(n))
@@ -377,9 +384,12 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
     dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
     stashed = bool(getattr(ws, "stashed", False))
-    ws.stashed = False  # the stash is converted in place: it can be consumed once
+    fused = stashed and cfg.fuse_scale  # convert the stash inside the gradient GEMMs instead of an HBM pass
     _mark("backward_begin")
-    if stashed:
+    if fused:
+        be.backward_factors(ws, t3, g3)
+    elif stashed:
+        ws.stashed = False  # converted in place: this stash can serve one backward only
         be.backward_scale(ws, t3, g3)
     else:
         be.backward_tiles(ws, t3, g3)
@@ -387,7 +397,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     col = None
     mult = 1.0
     if pb.world == 1:
-        be.backward_gemms(ws, t3, g3)
+        be.backward_gemms_role(ws, t3, g3, 0, fused)
         _mark("backward_gemms")
     else:
         import torch.distributed as dist
@@ -400,14 +410,14 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             _reduce_scatter([(col[m].view(-1), part[m].view(-1)) for m in range(3)], cfg.process_group, img.is_cuda)
 
         if not (cfg.overlap and img.is_cuda):
-            be.backward_gemms(ws, t3, g3)
+            be.backward_gemms_role(ws, t3, g3, 0, fused)
             _mark("backward_gemms")
             scatter()
             _mark("reduce_scatter")
         else:
             cur = torch.cuda.current_stream()
             comm = _comm_stream(img.device)
-            be.backward_gemms_role(ws, t3, g3, 1)  # column role first ...
+            be.backward_gemms_role(ws, t3, g3, 1, fused)  # column role first ...
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(comm):
@@ -417,7 +427,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
                 reduced.record(comm)
             prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
             try:
-                be.backward_gemms_role(ws, t3, g3, 2)
+                be.backward_gemms_role(ws, t3, g3, 2, fused)
             finally:
                 be.set_max_sms(prev)
             cur.wait_event(reduced)

@@ -26,6 +26,7 @@ namespace {
 constexpr int kMaxStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kMaxEpiWarps = 16;
+constexpr int kConvGroups = 4;   // groups of epilogue warps that take the conversion k blocks round-robin
 
 struct __align__(8) PipeBarriers {
   uint64_t full[kMaxStages];    // TMA -> MMA: operand bytes have landed (leader CTA's barrier collects both CTAs' bytes)
@@ -228,7 +229,7 @@ __device__ __forceinline__ uint32_t kernel_setup(PipeBarriers* bars, int warp, i
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
       mbar_init(&bars->afull[i], 1);
-      mbar_init(&bars->ready[i], CG * EW);
+      mbar_init(&bars->ready[i], CG * (EW / kConvGroups));
     }
 #pragma unroll
     for (int i = 0; i < kAccStages; ++i) {
@@ -830,14 +831,13 @@ __device__ __forceinline__ Tile decode_gemm(const GemmParams& P, int t) {
 
 // In-place conversion of one A tile (16 KiB, fp16, 128-byte swizzle) by the EW epilogue warps of a CTA:
 //   A(m, k) <- A(m, k) * (um[m] * wk[k] + um2[m] * wk2[k])
-// The tile is 1024 16-byte chunks; thread `tid` of the 32 EW handles chunks tid + 32 EW u.  Its chunk column c = tid & 7
+// The tile is 1024 16-byte chunks; thread `tid` of the NT that share a tile handles chunks tid + NT u.  Its chunk column c = tid & 7
 // is the same for every u, so for a K-major tile (rows = m, chunk = 8 consecutive k) the k factors are fixed per
 // thread and the m factors vary with u; for an MN-major tile (rows = k, two 64-wide m boxes, chunk = 8 consecutive m)
 // it is the other way round.
-template <int EW>
+template <int NT>                          // threads that share one tile: 64 .. 512
 struct TileConverter {
-  static constexpr int NT = 32 * EW;
-  static constexpr int CPT = 1024 / NT;   // chunks per thread: 4 (EW = 8) or 2 (EW = 16)
+  static constexpr int CPT = 1024 / NT;   // chunks per thread
   float fm[16], fm2[16];                  // m-side factors: K-major: [u] ; MN-major: [box][e]
 
   __device__ __forceinline__ void load_m(const float* um, const float* um2, int m0, int m_limit, int tid, bool a_mn) {
@@ -899,7 +899,7 @@ struct TileConverter {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float2 x = __half22float2(h[e]);
-          // g is compile-time after unrolling for EW = 8 (u >> 1) and EW = 16 (u)
+          // the box index (NT u) >> 9 is a compile-time constant after unrolling
           const int o = 8 * ((NT * u) >> 9) + 2 * e;
           x.x *= fmaf(fm[o], wk, fm2[o] * wk2);
           x.y *= fmaf(fm[o + 1], wk, fm2[o + 1] * wk2);
@@ -958,6 +958,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
     }
     int it = 0;
     RingState conv_ring;
+    uint32_t conv_count = 0;
     for (int t = cluster_id; t < total; t += num_clusters, ++it) {
       const Tile tile = decode_gemm<CG>(P, t);
       const int acc = it & 1;
@@ -970,10 +971,14 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
       float* out = P.out[j] + static_cast<size_t>(row) * P.ldc[j] + c0;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + slice * CS;
       {
-        // conversion segments: follow the producer's ring and convert this CTA's A tile of every k block in place
-        // (stash -> G', see backward_scale_kernel) before the MMA issuer may read it
+        // conversion segments: follow the producer's ring and convert this CTA's A tile in place (stash -> G', see
+        // backward_scale_kernel) before the MMA issuer may read it.  The warps form kConvGroups groups that take the
+        // k blocks round-robin, so the fixed per-block cost (barrier wait, proxy fence, arrive) is paid by EW /
+        // kConvGroups warps per block instead of all EW.
         const Job& job = P.jobs[j];
-        const int tid = warp * 32 + lane;
+        constexpr int kGroupWarps = EW / kConvGroups;
+        const int group = warp / kGroupWarps;
+        const int tid = (warp % kGroupWarps) * 32 + lane;
         const int m0_cta = tile.m0 + static_cast<int>(rank) * BM;
         for (int sg = 0; sg < job.nseg; ++sg) {
           const Segment seg = job.seg[sg];
@@ -983,17 +988,19 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
             for (int kb = kb_lo; kb < kb_hi; ++kb) conv_ring.advance(P.stages);
             continue;
           }
-          TileConverter<EW> cv;
+          TileConverter<32 * kGroupWarps> cv;
           cv.load_m(P.fac + seg.um_off, P.fac + seg.um2_off, m0_cta, P.m[j], tid, seg.a_mn != 0);
-          for (int kb = kb_lo; kb < kb_hi; ++kb) {
-            mbar_wait_bounded<false>(&bars.afull[conv_ring.stage], conv_ring.conv_parity(), 6);
-            uint8_t* sa = smem + conv_ring.stage * Geo<CG>::kStageBytes;
-            cv.convert(sa, reinterpret_cast<const float*>(sa + A_STAGE_BYTES + Geo<CG>::kBBytes), tid, seg.a_mn != 0);
-            fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 1 || rank == 0) mbar_arrive(&bars.ready[conv_ring.stage]);
-              else mbar_arrive_cluster(&bars.ready[conv_ring.stage], 0);
+          for (int kb = kb_lo; kb < kb_hi; ++kb, ++conv_count) {
+            if (conv_count % kConvGroups == group) {
+              mbar_wait_bounded<false>(&bars.afull[conv_ring.stage], conv_ring.conv_parity(), 6);
+              uint8_t* sa = smem + conv_ring.stage * Geo<CG>::kStageBytes;
+              cv.convert(sa, reinterpret_cast<const float*>(sa + A_STAGE_BYTES + Geo<CG>::kBBytes), tid, seg.a_mn != 0);
+              fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 1 || rank == 0) mbar_arrive(&bars.ready[conv_ring.stage]);
+                else mbar_arrive_cluster(&bars.ready[conv_ring.stage], 0);
+              }
             }
             conv_ring.conv_used();
             conv_ring.advance(P.stages);

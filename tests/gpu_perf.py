@@ -32,7 +32,7 @@ def step(b, d, iters):
     t3 = torch.full((3,), 2.6592, device="cuda")
     g3 = torch.ones(3, device="cuda")
     cfg = ops.TriContrastiveConfig(math="f16", stash={"1": True, "0": False}.get(os.environ.get("SCLIP_STASH", "auto"), "auto"),
-                                   fuse_scale=os.environ.get("SCLIP_FUSE", "1") == "1")
+                                   fuse_scale=os.environ.get("SCLIP_FUSE", "0") == "1")
     ms = timed(lambda: ops.forward_backward_raw(*ten, t3, g3, cfg), iters)
     marks = []
 

@@ -287,23 +287,37 @@ def main():
             ms = time_steps(resident_step, steps, warmup, dist if shard else None)
         stages = stage_breakdown(resident_step, min(steps, 5))
 
-        # end to end through the public autograd API with HOST buffers
+        # end to end through the public autograd API with HOST buffers: every step copies its three embedding matrices
+        # from pinned host memory and reads the three losses back.  Like a training loop with a prefetching loader, the
+        # copy of step n+1 is issued on a second stream while step n computes (two device buffer sets).
         host = [e.cpu().pin_memory() for e in embs]
-        dbuf = [torch.empty_like(e) for e in embs]
+        dbuf = [[torch.empty_like(e) for e in embs] for _ in range(2)]
         params = [torch.full((), LOGIT_SCALE_INIT, device=dev, requires_grad=True) for _ in range(3)]
         loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        arrived = [torch.cuda.Event(), torch.cuda.Event()]
+        state = {"cur": 0}
+
+        def prefetch(slot):
+            with torch.cuda.stream(copy_stream):
+                for h, dst in zip(host, dbuf[slot]):
+                    dst.copy_(h, non_blocking=True)
+                arrived[slot].record(copy_stream)
+
+        prefetch(0)
 
         def e2e_step():
-            leaves = []
-            for h, dst in zip(host, dbuf):
-                dst.copy_(h, non_blocking=True)
-                leaves.append(dst.detach().requires_grad_(True))
+            slot = state["cur"]
+            torch.cuda.current_stream().wait_event(arrived[slot])
+            prefetch(1 - slot)  # its previous consumer finished before the host sync at the end of the last step
+            leaves = [d.detach().requires_grad_(True) for d in dbuf[slot]]
             for p in params:
                 p.grad = None
             it, ta, ai = fused_tri_contrastive(*leaves, *params, config=cfg)
             (it + ta + ai).backward()
             loss_host.copy_(torch.stack([it.detach(), ta.detach(), ai.detach()]), non_blocking=True)
             torch.cuda.current_stream().synchronize()  # the caller reads the losses (main_pretraining.py:169-170)
+            state["cur"] = 1 - slot
 
         ms_e2e = time_steps(e2e_step, steps, warmup, dist if shard else None)
         h2d = sum(h.numel() * h.element_size() for h in host)

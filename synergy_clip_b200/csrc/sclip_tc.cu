@@ -366,6 +366,13 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// saturating variant: values above 65504 (a stash element more than ~14 nats above both positive pairs) clamp
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 constexpr int kSlabBytes = BM * 64 * 2;  // one 128-row x 64-column fp16 slab (16 KiB) staged for a TMA store
 
 // ============================================================================================== forward tiles
@@ -432,10 +439,28 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
     const int slice = warp >> 2;   // which CS accumulator columns
     const int epi_tid = warp * 32 + lane;
     const int col0 = slice * CS;
+    // positive-pair logits of the rows / columns a tile touches (stash scaling), loaded one tile ahead
+    constexpr int kDiagCols = (BN + static_cast<int>(kEpiThreads) - 1) / static_cast<int>(kEpiThreads);
+    float pre_r[4] = {0.f, 0.f, 0.f, 0.f};
+    float pre_c[kDiagCols] = {};
+    bool pre_valid = false;
+    auto load_diag = [&](int pp, int wr0, int nn0, float (&r4)[4], float (&c1)[kDiagCols]) {
+      const float* dg = P.diag_all + static_cast<size_t>(pp) * P.rows_global;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = wr0 + 16 * (j >> 1) + 8 * (j & 1) + (lane >> 2);
+        r4[j] = row < P.rows_local ? dg[P.row_offset + row] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kDiagCols; ++u) {
+        const int cc = epi_tid + u * kEpiThreads;
+        c1[u] = (cc < BN && nn0 + cc < P.rows_global) ? dg[nn0 + cc] : 0.f;
+      }
+    };
     int it = 0;
     for (int t = cluster_id; t < total; t += num_clusters, ++it) {
       Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
-        tile.job = P.pair_list[tile.job];
+      tile.job = P.pair_list[tile.job];
       const int acc = it & 1;
       const int p = tile.job;
       const int ti = tile.ti * CG + static_cast<int>(rank);  // 128-row tile index of this CTA
@@ -447,17 +472,26 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       const bool edge = (m0 + BM > P.rows_local) || (n0 + BN > P.rows_global);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
 
-      // stash scaling: E~_ij = 2^(acc c - h_i - h_j), h = (L_ii / 2) log2(e) + 2, prepared while the MMAs run
+      // stash scaling: E~_ij = 2^(acc c - h_i - h_j), h = (L_ii / 2) log2(e) + 2.  While s < 64 the exponential E of
+      // the statistics is reused: E~ = E sigma_i tau_j with sigma = 2^-h_i, tau = 2^-h_j (two multiplies instead of a
+      // second exponential); above, E is relative to the tile maximum and E~ gets its own exponential.
+      // The positive-pair logits were prefetched during the previous tile (pre_r / pre_c).
+      const bool fast_tile = s < kFastPathMaxScale;
       float hr[4] = {0.f, 0.f, 0.f, 0.f};
       if (P.stash) {
-        const float* dg = P.diag_all + static_cast<size_t>(p) * P.rows_global;
+        if (!pre_valid) load_diag(p, wrow0, n0, pre_r, pre_c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int row = wrow0 + 16 * (j >> 1) + 8 * (j & 1) + (lane >> 2);
-          hr[j] = row < P.rows_local ? fmaf(0.5f * kLog2e, dg[P.row_offset + row], 2.0f) : 0.f;
+          const float h = fmaf(0.5f * kLog2e, pre_r[j], 2.0f);
+          hr[j] = fast_tile ? ex2_approx(-h) : h;
         }
-        for (int cc = epi_tid; cc < BN; cc += kEpiThreads)
-          colh[acc][cc] = (n0 + cc < P.rows_global) ? fmaf(0.5f * kLog2e, dg[n0 + cc], 2.0f) : 0.f;
+#pragma unroll
+        for (int u = 0; u < kDiagCols; ++u) {
+          const float h = fmaf(0.5f * kLog2e, pre_c[u], 2.0f);
+          if (epi_tid + u * kEpiThreads < BN) colh[acc][epi_tid + u * kEpiThreads] = fast_tile ? ex2_approx(-h) : h;
+        }
+        // every staging slab was handed to a TMA store one tile ago: make sure those stores have read it
+        if ((epi_tid & 127) == 0) tma_store_wait_read<0>();
         named_bar_sync(kBarAll, kEpiThreads);
       }
 
@@ -507,6 +541,15 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       uint32_t va[32];
       [[maybe_unused]] uint32_t vb[32];
       auto process = [&](uint32_t (&v)[32], int ch, uint8_t* stash_slab = nullptr, int hc = 0) {
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), c, -ref2));
+        const int gcol0 = n0 + col0 + ch * 32;          // first global column of the block
+        if (edge) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!((wrow0 + frag_row(i, lane)) < P.rows_local && (gcol0 + frag_col(i, lane)) < P.rows_global)) e[i] = 0.f;
+        }
         if (stash_slab != nullptr) {
           float cf[8];
 #pragma unroll
@@ -522,22 +565,19 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
               const int i0 = 16 * (gh >> 1) + 4 * n + 2 * (gh & 1);
-              const float s0 = ex2_approx(fmaf(__uint_as_float(v[i0]), c, -(hr[gh] + cf[2 * n])));
-              const float s1 = ex2_approx(fmaf(__uint_as_float(v[i0 + 1]), c, -(hr[gh] + cf[2 * n + 1])));
+              float s0, s1;
+              if (fast_tile) {
+                s0 = e[i0] * (hr[gh] * cf[2 * n]);
+                s1 = e[i0 + 1] * (hr[gh] * cf[2 * n + 1]);
+              } else {
+                s0 = ex2_approx(fmaf(__uint_as_float(v[i0]), c, -(hr[gh] + cf[2 * n])));
+                s1 = ex2_approx(fmaf(__uint_as_float(v[i0 + 1]), c, -(hr[gh] + cf[2 * n + 1])));
+              }
               const int chunk16 = hc * 4 + n;
               const uint32_t off = r_in_tile * 128 + ((chunk16 ^ (r_in_tile & 7)) << 4) + 4 * (lane & 3);
-              *reinterpret_cast<uint32_t*>(stash_slab + off) = pack_half2(fminf(s0, 65504.f), fminf(s1, 65504.f));
+              *reinterpret_cast<uint32_t*>(stash_slab + off) = pack_half2_sat(s0, s1);
             }
           }
-        }
-        float e[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), c, -ref2));
-        const int gcol0 = n0 + col0 + ch * 32;          // first global column of the block
-        if (edge) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (!((wrow0 + frag_row(i, lane)) < P.rows_local && (gcol0 + frag_col(i, lane)) < P.rows_global)) e[i] = 0.f;
         }
         const int grow0 = P.row_offset + wrow0;         // global index of the block's first row
         if (grow0 < gcol0 + 32 && gcol0 < grow0 + 32) {  // the block touches the diagonal: positive-pair logits
@@ -558,11 +598,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
 #pragma unroll
         for (int sl = 0; sl < NSLAB; ++sl) {
           uint8_t* slab = staging + (slice * NSLAB + sl) * kSlabBytes;  // one buffer per slab, reused one tile later
-          if (slice_tid == 0) {
-            if (NSLAB == 1) tma_store_wait_read<0>();
-            else tma_store_wait_read<NSLAB - 1>();
-          }
-          named_bar_sync(kBarSlice + slice, 128);
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {
             const int ch = sl * 2 + hc;
@@ -601,6 +636,13 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
         }
       }
       release_accumulator<CG>(&bars, acc, rank, lane);  // all TMEM reads of this warp are complete
+      pre_valid = false;
+      if (P.stash && t + num_clusters < total) {  // start the next tile's diagonal loads under this tile's tail
+        Tile nx = decode_similarity<CG>(t + num_clusters, nti_c, P.tj_count, P.tj_begin);
+        const int np = P.pair_list[nx.job];
+        load_diag(np, (nx.ti * CG + static_cast<int>(rank)) * BM + q * 32, nx.n0, pre_r, pre_c);
+        pre_valid = true;
+      }
       {
         int r;
         const float rsum = frag_row_sum(rp, lane, r);

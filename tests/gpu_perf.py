@@ -34,6 +34,14 @@ def step(b, d, iters):
     cfg = ops.TriContrastiveConfig(math="f16", stash={"1": True, "0": False}.get(os.environ.get("SCLIP_STASH", "auto"), "auto"),
                                    fuse_scale=os.environ.get("SCLIP_FUSE", "0") == "1")
     ms = timed(lambda: ops.forward_backward_raw(*ten, t3, g3, cfg), iters)
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        ops.forward_backward_raw(*ten, t3, g3, cfg)
+    host_ms = (time.perf_counter() - t0) / iters * 1e3  # enqueue time only (no sync inside the loop)
+    torch.cuda.synchronize()
+    print(f"HOST enqueue {host_ms:.3f} ms/step", flush=True)
     marks = []
 
     def trace(name):

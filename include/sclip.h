@@ -71,7 +71,7 @@ typedef struct sclip_layout {
                              sclip_prologue at row_offset [exchange: all-gather of the row shards]           */
   uint64_t xhat_lo;       /* same shape, low halves (SCLIP_MATH_F16X3 only, else == xhat)                    */
   uint64_t inv_norm;      /* [3][rows_local] fp32                                                            */
-  uint64_t row_part;      /* [3][col_tiles][rows_local] fp32 partial row sums                                */
+  uint64_t row_part;      /* [3][col_tiles][2][rows_local] fp32 partial row sums (per 128-column slice)      */
   uint64_t col_part;      /* [3][row_tiles][rows_global] fp32 partial column sums                            */
   uint64_t tile_ref;      /* [3][row_tiles][col_tiles] fp32 exponent reference of each tile                  */
   uint64_t diag;          /* [3][rows_local] fp32 positive-pair logits L_ii                                  */

@@ -48,6 +48,7 @@ struct Segment {
   // with the four factor vectors at these float offsets from GemmParams::fac (k vectors padded to 64 floats)
   int transform;
   int um_off, um2_off, wk_off, wk2_off;
+  int map_a64;  // K-major A operand with a 64-row box (multicast halves of the wide GEMM tiles); -1 if unused
 };
 
 struct Job {
@@ -125,6 +126,7 @@ struct FwdParams {
   int store_map[3];          // tensor maps (box 64 x 128) of the stash strips
   const float* diag_all;     // [3][rows_global] positive-pair logits (stash scaling)
   int stages;       // depth of the TMA ring
+  int pair_filter;  // forward_tiles_kernel: skip the pairs forward_fast_kernel has taken (s < 44)
   int debug;        // profiling experiments only (SCLIP_DEBUG): 1 = epilogue releases the accumulator untouched,
                     // 2 = epilogue only loads the accumulator from TMEM
   float acc_scale;  // accumulator -> cosine (1 in F16 mode, 2^-16 in F16X3 mode)
@@ -158,6 +160,7 @@ struct GemmParams {
   int njobs;
   int total_tiles;
   int stages;
+  int wn;            // wide kernel: accumulator columns of one CTA-pair tile (256 | 384 | 512)
   const float* fac;  // base of the conversion factor vectors (Segment::transform)
   const float* t3;   // when non-null alpha = alpha0 * max_q |exp(t_q) g_q| (backward); else alpha = alpha0
   const float* g3;
@@ -169,6 +172,9 @@ struct GemmParams {
 int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream);
 int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t stream);
 int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream);
+// CTA pairs on 256 x wn tiles with one accumulator (MN-major B operands only); see gemm_wide_kernel
+int launch_gemm_wide(const GemmParams& p, int ew, cudaStream_t stream);
+int wide_stages(int wn);  // depth of the TMA ring that fits beside nothing else in shared memory
 int cta_group();   // SCLIP_CTA_GROUP environment override (1 or 2), default 2
 int epi_warps();   // SCLIP_EPI_WARPS environment override (8 or 16), default 16
 int max_sms();     // sclip_set_max_sms (0 = all)

@@ -55,6 +55,50 @@ int ring_stages(int slabs) {
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// The gradient GEMMs run on 256 x wn CTA-pair tiles (gemm_wide_kernel) unless SCLIP_WIDE=0 or SCLIP_CTA_GROUP=1.
+bool wide_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("SCLIP_WIDE");
+    cached = (cta_group() == 2 && !(e != nullptr && e[0] == '0')) ? 1 : 0;
+  }
+  return cached != 0;
+}
+
+// accumulator columns per tile: the fewest tiles of at most 512 columns, rounded to whole 64-column boxes per CTA
+int wide_width(int n) {
+  const int nt = ceil_div(n, 512);
+  const int w = ceil_div(ceil_div(n, nt), 128) * 128;
+  return w < 256 ? 256 : w;
+}
+
+// k splits per tile so that the persistent clusters finish together: minimise rounds x (k blocks per unit + fixed
+// cost of a unit: ring fill and epilogue, about 8 k-block times), keeping at least 32 k blocks per unit
+int wide_ksplits(int tiles, int kb) {
+  int sms = 148;
+  {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+  }
+  if (max_sms() > 0 && max_sms() < sms) sms = max_sms();
+  const int clusters = sms / 2 > 0 ? sms / 2 : 1;
+  const char* e = getenv("SCLIP_KSPLITS");  // profiling experiments only
+  if (e != nullptr && atoi(e) >= 1) return atoi(e);
+  int best = 1;
+  double best_cost = 0;
+  for (int ks = 1; ks <= 8; ++ks) {
+    if (ks > 1 && kb / ks < 32) break;
+    const double cost = static_cast<double>(ceil_div(tiles * ks, clusters)) * (ceil_div(kb, ks) + 8);
+    if (ks == 1 || cost < best_cost * 0.995) {
+      best = ks;
+      best_cost = cost;
+    }
+  }
+  return best;
+}
+
 int check_problem(const sclip_problem* pb) {
   if (pb == nullptr) {
     set_error("problem is null");
@@ -108,7 +152,7 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->xhat = take(3 * bg * d * 2);
   lay->xhat_lo = x3 ? take(3 * bg * d * 2) : lay->xhat;
   lay->inv_norm = take(3 * bl * 4);
-  lay->row_part = take(3 * ntj * bl * 4);
+  lay->row_part = take(3 * 2 * ntj * bl * 4);
   lay->col_part = take(3 * nti * bg * 4);
   lay->tile_ref = take(3 * nti * ntj * 4);
   lay->diag = take(3 * bl * 4);
@@ -285,7 +329,9 @@ struct MapTable {
   }
 };
 
-Segment seg(int a, int b, int a_mn, int b_mn, int num_kb) { return Segment{a, b, a_mn, b_mn, num_kb, 0, 0, 0, 0, 0}; }
+Segment seg(int a, int b, int a_mn, int b_mn, int num_kb, int a64 = -1) {
+  return Segment{a, b, a_mn, b_mn, num_kb, 0, 0, 0, 0, 0, a64};
+}
 
 // similarity job of pair p (forward and the backward recompute)
 void similarity_job(const Workspace& w, MapTable& t, int p, Job* job) {
@@ -541,7 +587,8 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
         job.seg[job.nseg++] = seg(tab.use(kGloK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
         job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
       }
-      job.seg[job.nseg++] = conv(seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g), pr, true);
+      // (the 64 x 64 box map of the MN-major view doubles as the 64-row K-major box of the multicast halves)
+      job.seg[job.nseg++] = conv(seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g, tab.use(kGMN + pr)), pr, true);
     } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
       const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
       if (x3) {
@@ -584,6 +631,34 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
   }
   if (tab.rc) return tab.rc;
   p.njobs = nj;
+  if (wide_enabled() && !x3 && !convert) {
+    // 256 x wn tiles, k split so that the clusters finish together; split partial sums are added into zeroed outputs
+    p.wn = wide_width(pb.dim);
+    int kb_max = 0, base_tiles = 0;
+    for (int j = 0; j < nj; ++j) {
+      Job& job = p.jobs[j];
+      job.n_tiles = ceil_div(pb.dim, p.wn);
+      int kb = 0;
+      for (int s = 0; s < job.nseg; ++s) kb += job.seg[s].num_kb;
+      kb_max = kb > kb_max ? kb : kb_max;
+      base_tiles += job.m_tiles * job.n_tiles;
+    }
+    const int ks = wide_ksplits(base_tiles, kb_max);
+    tiles = 0;
+    for (int j = 0; j < nj; ++j) {
+      Job& job = p.jobs[j];
+      job.ksplits = ks;
+      job.tile_base = tiles;
+      tiles += job.m_tiles * job.n_tiles * ks;
+    }
+    if (ks > 1) {
+      if (do_row) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_row, 0, 3 * bl * d * 4, st));
+      if (do_col) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
+    }
+    p.total_tiles = tiles;
+    p.stages = wide_stages(p.wn);
+    return launch_gemm_wide(p, epi_warps(), st);
+  }
   p.total_tiles = tiles;
   p.stages = ring_stages(0);
   return launch_gemm(p, cta_group(), epi_warps(), st);
@@ -664,7 +739,9 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
     rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN / cta_group());
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK), 0, 0, 0, 0, 0};
+  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK), 0, 0, 0, 0, 0, 2};
+  if (!a_mn) rc = make_map(&p.maps[2], a, k, m, lda, BK, 64);  // 64-row boxes (multicast halves of the wide tiles)
+  if (rc) return rc;
   p.jobs[0].nseg = 1;
   p.jobs[0].ksplits = 1;
   p.jobs[0].m_tiles = ceil_div(m, BM * cta_group());
@@ -675,8 +752,24 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
   p.m[0] = m;
   p.n[0] = n;
   p.njobs = 1;
-  p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles;
   p.alpha0 = alpha;
+  if (wide_enabled() && b_mn && n > 256) {
+    p.wn = wide_width(n);
+    p.jobs[0].n_tiles = ceil_div(n, p.wn);
+    const int ks = wide_ksplits(p.jobs[0].m_tiles * p.jobs[0].n_tiles, ceil_div(k, BK));
+    p.jobs[0].ksplits = ks;
+    if (ks > 1) {
+      if (ldc != n) {
+        set_error("sclip_gemm_f16: a k-split launch needs a dense output (ldc == n)");
+        return SCLIP_ERR_ARGUMENT;
+      }
+      SCLIP_CUDA_OK(cudaMemsetAsync(c, 0, static_cast<size_t>(m) * n * 4, st));
+    }
+    p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles * ks;
+    p.stages = wide_stages(p.wn);
+    return launch_gemm_wide(p, epi_warps(), st);
+  }
+  p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles;
   p.stages = ring_stages(0);
   return launch_gemm(p, cta_group(), epi_warps(), st);
 }

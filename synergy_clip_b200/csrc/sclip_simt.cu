@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a)
     float R = -INFINITY;
     for (int tj = 0; tj < a.ntj; ++tj) R = fmaxf(R, ref[tj]);
     float sum = 0.f;
-    for (int tj = 0; tj < a.ntj; ++tj)
-      sum += a.row_part[(static_cast<size_t>(p) * a.ntj + tj) * a.rows_local + i] * __expf(ref[tj] - R);
+    for (int tj = 0; tj < a.ntj; ++tj) {  // two slots per column tile (one per 128-column slice)
+      const float* rp = a.row_part + (static_cast<size_t>(p) * a.ntj * 2 + tj * 2) * a.rows_local + i;
+      sum += (rp[0] + rp[a.rows_local]) * __expf(ref[tj] - R);
+    }
     const float lse = R + logf(sum);
     a.lse_row[static_cast<size_t>(p) * a.rows_local + i] = lse;
     a.row_inv[static_cast<size_t>(p) * a.rows_local + i] = 1.0f / sum;  // meaningful when every tile reference is 0

@@ -13,6 +13,7 @@
 // (the two single-thread roles sit on the highest warp ids: the warp scheduler favours higher ids, and a delayed
 //  TMA / MMA issue stalls the whole SM while a delayed epilogue warp does not)
 // The 512 TMEM columns hold two 128x256 fp32 accumulators, so the epilogue of tile n runs under the MMAs of tile n+1.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -376,6 +377,21 @@ __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
 constexpr int kSlabBytes = BM * 64 * 2;  // one 128-row x 64-column fp16 slab (16 KiB) staged for a TMA store
 
 // ============================================================================================== forward tiles
+// Pairs whose scale allows the folded-exponent epilogue of forward_fast_kernel: |L| <= s < 44 keeps
+// 2^(c acc - h_i), h_i = (L_ii / 2) log2(e) + 2, and its row / column sums inside the normal fp32 range.
+constexpr float kFoldMaxScale = 44.0f;
+
+// pairs handled by a launch: those of P.pair_list with (fast ? s_p < kFoldMaxScale : s_p >= kFoldMaxScale)
+__device__ __forceinline__ int select_pairs(const FwdParams& P, bool fast, int (&list)[3]) {
+  int n = 0;
+  for (int u = 0; u < P.npairs; ++u) {
+    const int p = P.pair_list[u];
+    const bool is_fast = expf(P.t3[p]) < kFoldMaxScale;
+    if (is_fast == fast) list[n++] = p;
+  }
+  return n;
+}
+
 template <int CG>
 __device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int tj_begin = 0) {
   Tile r;
@@ -408,7 +424,10 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
   const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
   const int nti_c = P.nti / CG;
-  const int total = P.npairs * nti_c * P.tj_count;
+  // pair_filter: the pairs with s < kFoldMaxScale were taken by forward_fast_kernel
+  int pairs[3] = {P.pair_list[0], P.pair_list[1], P.pair_list[2]};
+  const int npairs = P.pair_filter ? select_pairs(P, false, pairs) : P.npairs;
+  const int total = npairs * nti_c * P.tj_count;
 
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
@@ -417,7 +436,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       RingState rs;
       for (int t = cluster_id; t < total; t += num_clusters) {
         Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
-        tile.job = P.pair_list[tile.job];
+        tile.job = pairs[tile.job];
         producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
       }
     }
@@ -428,7 +447,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
         Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
-        tile.job = P.pair_list[tile.job];
+        tile.job = pairs[tile.job];
         const int acc = it & 1;
         mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
       }
@@ -460,7 +479,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
     int it = 0;
     for (int t = cluster_id; t < total; t += num_clusters, ++it) {
       Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
-      tile.job = P.pair_list[tile.job];
+      tile.job = pairs[tile.job];
       const int acc = it & 1;
       const int p = tile.job;
       const int ti = tile.ti * CG + static_cast<int>(rank);  // 128-row tile index of this CTA
@@ -639,7 +658,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       pre_valid = false;
       if (P.stash && t + num_clusters < total) {  // start the next tile's diagonal loads under this tile's tail
         Tile nx = decode_similarity<CG>(t + num_clusters, nti_c, P.tj_count, P.tj_begin);
-        const int np = P.pair_list[nx.job];
+        const int np = pairs[nx.job];
         load_diag(np, (nx.ti * CG + static_cast<int>(rank)) * BM + q * 32, nx.n0, pre_r, pre_c);
         pre_valid = true;
       }
@@ -658,11 +677,337 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
         float rs = 0.f;
 #pragma unroll
         for (int u = 0; u < S; ++u) rs += rowacc[acc][u][epi_tid];
-        P.row_part[(static_cast<size_t>(p) * P.ntj + tj) * P.rows_local + m0 + epi_tid] = rs;
+        // two slots per column tile (forward_fast_kernel writes one per column slice)
+        P.row_part[(static_cast<size_t>(p) * P.ntj * 2 + tj * 2) * P.rows_local + m0 + epi_tid] = rs;
+        P.row_part[(static_cast<size_t>(p) * P.ntj * 2 + tj * 2 + 1) * P.rows_local + m0 + epi_tid] = 0.f;
       }
       if (epi_tid == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = ref2 / kLog2e;
     }
     if (P.stash && (epi_tid & 127) == 0) tma_store_wait_all<0>();
+  }
+  kernel_teardown<CG, EW>(tmem_base, warp);
+}
+
+// ============================================================================================== fast forward tiles
+// The forward tile kernel for the common case s = exp(logit_scale) < 64 (no exponent reference), CTA pairs, 8 epilogue
+// warps.  Same mainloop; the epilogue is rebuilt around what bounded the generic one (17 instructions per logit,
+// two all-warp barriers per tile):
+//   * packed fp32 pairs (FFMA2 / FADD2 / FMUL2) on the two adjacent columns every thread owns,
+//   * the row factor of the stash folded into the exponent: e' = 2^(c acc - h_i) = E sigma_i feeds the row sums
+//     (scaled back once per row), the column sums (FFMA2 with weight 1 / sigma_i) and the stash E~ = e' tau_j,
+//   * stmatrix for the fp16 staging (one instruction per 8 x 32 block instead of four stores),
+//   * no all-warp barrier: column statistics are combined by the four warps that share a column slice, the two
+//     column slices of a row write separate row partials, the column factors of tile n + 1 are staged during tile n,
+//     and a staging slab is reused two slabs later (the storing thread drains its bulk reads before the barrier).
+// Pairs with s >= kFoldMaxScale are left to forward_tiles_kernel (pair_filter).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void stmatrix_x4(uint32_t smem_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3)
+               : "memory");
+}
+
+template <bool STASH>
+__global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __grid_constant__ FwdParams P) {
+  constexpr int CG = 2, EW = 8;
+  constexpr int CS = BN / 2;       // columns per slice (two slices of four warps)
+  constexpr int NCH = CS / 32;     // 32-column chunks per warp and tile
+  __shared__ PipeBarriers bars;
+  __shared__ float colacc[kAccStages][4][BN];
+  __shared__ __align__(8) float coltau[kAccStages][BN];
+  uint8_t* smem = aligned_dyn_smem();
+  uint8_t* staging = smem + P.stages * Geo<CG>::kStageBytes;  // STASH: 2 slices x 2 slabs of 16 KiB
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+  const int nti_c = P.nti / CG;
+  int pairs[3];
+  const int npairs = select_pairs(P, true, pairs);
+  const int total = npairs * nti_c * P.tj_count;
+
+  const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
+
+  if (warp == EW) {
+    if (lane == 0) {
+      RingState rs;
+      for (int t = cluster_id; t < total; t += num_clusters) {
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        tile.job = pairs[tile.job];
+        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
+      }
+    }
+    __syncwarp();
+  } else if (warp == EW + 1) {
+    if (lane == 0 && rank == 0) {
+      RingState rs;
+      int it = 0;
+      for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        tile.job = pairs[tile.job];
+        const int acc = it & 1;
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;        // TMEM lane quarter
+    const int slice = warp >> 2;   // column half of the tile
+    const int slice_tid = (warp & 3) * 32 + lane;
+    const int col0 = slice * CS;
+    const int my_col = col0 + slice_tid;  // the tile column whose factor / statistics this thread stages
+    // stmatrix row addresses: lane L supplies row (L & 7) of 8 x 8 matrix (L >> 3) = 16-byte chunk (L >> 3) of the
+    // 64-byte block; rows 128 bytes apart, chunk index XOR row & 7 (the TMA 128-byte swizzle)
+    const uint32_t st_row = static_cast<uint32_t>(q * 32 + (lane & 7)) * 128u;
+    const uint32_t st_chunk0 = static_cast<uint32_t>(((lane >> 3) ^ (lane & 7)) << 4);
+    const uint32_t st_chunk1 = static_cast<uint32_t>((((lane >> 3) + 4) ^ (lane & 7)) << 4);
+
+    // positive-pair logits of a tile's rows / columns -> stash factors (loaded one tile ahead)
+    auto tile_coords = [&](int t, int& p, int& ti, int& tj, int& m0, int& n0) {
+      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+      p = pairs[tile.job];
+      ti = tile.ti * CG + static_cast<int>(rank);
+      tj = tile.tj;
+      m0 = ti * BM;
+      n0 = tile.n0;
+    };
+    auto load_diag = [&](int t, float (&r4)[4], float& c1) {
+      int p, ti, tj, m0, n0;
+      tile_coords(t, p, ti, tj, m0, n0);
+      const float* dg = P.diag_all + static_cast<size_t>(p) * P.rows_global;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = m0 + q * 32 + 16 * (j >> 1) + 8 * (j & 1) + (lane >> 2);
+        r4[j] = row < P.rows_local ? dg[P.row_offset + row] : 0.f;
+      }
+      c1 = (n0 + my_col < P.rows_global) ? dg[n0 + my_col] : 0.f;
+    };
+    float nxt_r[4] = {0.f, 0.f, 0.f, 0.f}, nxt_c = 0.f;  // raw positive-pair logits of the next tile
+    float cur_r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (STASH && cluster_id < total) {
+      float c1;
+      load_diag(cluster_id, cur_r, c1);
+      coltau[0][my_col] = ex2_approx(-fmaf(0.5f * kLog2e, c1, 2.0f));
+    }
+    named_bar_sync(kBarSlice + slice, 128);
+
+    int it = 0;
+    for (int t = cluster_id; t < total; t += num_clusters, ++it) {
+      int p, ti, tj, m0, n0;
+      tile_coords(t, p, ti, tj, m0, n0);
+      const int acc = it & 1;
+      const float s = expf(P.t3[p]);
+      const float c = s * kLog2e * P.acc_scale;  // accumulator -> logit in log2 units
+      const int wrow0 = m0 + q * 32;
+      const bool edge = (m0 + BM > P.rows_local) || (n0 + BN > P.rows_global);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0;
+      const bool has_next = t + num_clusters < total;
+      if (STASH && has_next) load_diag(t + num_clusters, nxt_r, nxt_c);
+
+      // h_i = (L_ii / 2) log2(e) + 2: e' = 2^(c acc - h_i) = E sigma_i;  isig = 1 / sigma_i restores E in the sums
+      uint64_t nh2[4], isig2[4];
+      float isig[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float h = STASH ? fmaf(0.5f * kLog2e, cur_r[j], 2.0f) : 0.f;
+        nh2[j] = pack2(-h, -h);
+        isig[j] = STASH ? ex2_approx(h) : 1.0f;
+        isig2[j] = pack2(isig[j], isig[j]);
+      }
+      const uint64_t c2 = pack2(c, c);
+
+      mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
+      tc_fence_after();
+      if (P.debug != 0) {  // profiling experiments: 1 = mainloop without the epilogue, 2 / 3 = only the TMEM loads
+        if (P.debug >= 2) {    //                        (2: 16x256b fragments, 3: 32x32b rows)
+          uint32_t v[32];
+          uint32_t sink = 0;
+          for (int ch = 0; ch < NCH; ++ch) {
+            if (P.debug == 2) tmem_ld_block32(taddr + ch * 32, v);
+            else tmem_ld_32x32b_x32(taddr + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sink ^= v[i];
+          }
+          if (sink == 0x12345678u) P.tile_ref[0] = 1.f;
+        }
+        release_accumulator<CG>(&bars, acc, rank, lane);
+        continue;
+      }
+
+      uint64_t rp2[4] = {0ull, 0ull, 0ull, 0ull};  // row partials (pairs of adjacent columns), in e' units
+      uint32_t va[32], vb[32];
+      auto process = [&](uint32_t (&v)[32], int ch) {
+        const int gcol0 = n0 + col0 + ch * 32;  // first global column of the block
+        const int grow0 = P.row_offset + wrow0;
+        if (grow0 < gcol0 + 32 && gcol0 < grow0 + 32) {  // the block touches the diagonal: positive-pair logits
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (grow0 + frag_row(i, lane) == gcol0 + frag_col(i, lane) && (wrow0 + frag_row(i, lane)) < P.rows_local)
+              P.diag[static_cast<size_t>(p) * P.rows_local + wrow0 + frag_row(i, lane)] =
+                  __uint_as_float(v[i]) * s * P.acc_scale;
+        }
+        uint64_t e2[16];  // e2[8 g + 2 n + h] = columns (8 n + 2 (lane % 4), + 1) of row 16 g + 8 h + lane / 4
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int i = 16 * g + 4 * n + 2 * h;
+              const uint64_t x = ffma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nh2[2 * g + h]);
+              float x0, x1;
+              unpack2(x, x0, x1);
+              e2[8 * g + 2 * n + h] = pack2(ex2_approx(x0), ex2_approx(x1));
+            }
+        if (edge) {  // ragged last row / column tile: entries outside the matrix contribute nothing
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int i = 16 * g + 4 * n + 2 * h;
+                float e0, e1;
+                unpack2(e2[8 * g + 2 * n + h], e0, e1);
+                const bool rok = (wrow0 + frag_row(i, lane)) < P.rows_local;
+                if (!(rok && (gcol0 + frag_col(i, lane)) < P.rows_global)) e0 = 0.f;
+                if (!(rok && (gcol0 + frag_col(i + 1, lane)) < P.rows_global)) e1 = 0.f;
+                e2[8 * g + 2 * n + h] = pack2(e0, e1);
+              }
+        }
+        // row partials and column partials (weights 1 / sigma_i turn e' back into E)
+        uint64_t cp2[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          cp2[n] = fmul2(e2[2 * n], isig2[0]);
+          cp2[n] = ffma2(e2[2 * n + 1], isig2[1], cp2[n]);
+          cp2[n] = ffma2(e2[8 + 2 * n], isig2[2], cp2[n]);
+          cp2[n] = ffma2(e2[8 + 2 * n + 1], isig2[3], cp2[n]);
+        }
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t a = fadd2(e2[8 * g + h], e2[8 * g + 2 + h]);
+            const uint64_t b = fadd2(e2[8 * g + 4 + h], e2[8 * g + 6 + h]);
+            rp2[2 * g + h] = fadd2(rp2[2 * g + h], fadd2(a, b));
+          }
+        if constexpr (STASH) {
+          // E~ = e' tau_j, packed to fp16 and staged through stmatrix in the TMA store's swizzled layout
+          uint8_t* slab = staging + (slice * 2 + (ch >> 1)) * kSlabBytes;
+          const uint32_t slab_addr = smem_u32(slab) + st_row + ((ch & 1) ? st_chunk1 : st_chunk0);
+          uint64_t tau2[4];
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            tau2[n] = *reinterpret_cast<const uint64_t*>(&coltau[acc][col0 + ch * 32 + 8 * n + 2 * (lane & 3)]);
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[4];
+#pragma unroll
+              for (int n = 0; n < 4; ++n) {
+                float s0, s1;
+                unpack2(fmul2(e2[8 * g + 2 * n + h], tau2[n]), s0, s1);
+                r[n] = pack_half2_sat(s0, s1);
+              }
+              stmatrix_x4(slab_addr + static_cast<uint32_t>(16 * g + 8 * h) * 128u, r[0], r[1], r[2], r[3]);
+            }
+        }
+        // column sums of the 32 rows: reduce-scatter of the 8 partials over the 8 lanes that share lane % 4
+        float cp[8];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) unpack2(cp2[n], cp[2 * n], cp[2 * n + 1]);
+#pragma unroll
+        for (int w = 16, half = 4; half >= 1; w >>= 1, half >>= 1) {
+          const bool up = (lane & w) != 0;
+#pragma unroll
+          for (int k = 0; k < half; ++k) {
+            const float send = up ? cp[k] : cp[k + half];
+            const float keep = up ? cp[k + half] : cp[k];
+            cp[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+          }
+        }
+        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        colacc[acc][q][col0 + ch * 32 + 8 * (idx >> 1) + 2 * (lane & 3) + (idx & 1)] = cp[0];
+      };
+
+      // software pipeline over the four chunks: the TMEM load of chunk ch + 1 is in flight while chunk ch is processed
+      tmem_ld_block32(taddr, va);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        tmem_ld_wait();
+        if (ch & 1) {
+          if (ch + 1 < NCH) tmem_ld_block32(taddr + (ch + 1) * 32, va);
+          else release_accumulator<CG>(&bars, acc, rank, lane);  // all TMEM reads of this warp are complete
+          process(vb, ch);
+        } else {
+          tmem_ld_block32(taddr + (ch + 1) * 32, vb);
+          process(va, ch);
+        }
+        if (ch == 1 && STASH && has_next)  // column factors of the next tile (ordered by the slab barriers below)
+          coltau[acc ^ 1][my_col] = ex2_approx(-fmaf(0.5f * kLog2e, nxt_c, 2.0f));
+        if (ch & 1) {  // a 64-column slab of this slice is staged (or, without stash, just keep the slices in step)
+          if constexpr (STASH) {
+            fence_proxy_async_smem();
+            if (slice_tid == 0) tma_store_wait_read<0>();  // every earlier slab store has left shared memory
+          }
+          named_bar_sync(kBarSlice + slice, 128);
+          if constexpr (STASH) {
+            if (slice_tid == 0) {
+              const int gcol = n0 + col0 + (ch >> 1) * 64;
+              if (gcol < P.rows_global)
+                tma_store_2d(&P.maps[P.store_map[p]], staging + (slice * 2 + (ch >> 1)) * kSlabBytes, gcol, m0);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      // column statistics of this slice: the four lane quarters are complete after the last slab barrier
+      if (n0 + my_col < P.rows_global)
+        P.col_part[(static_cast<size_t>(p) * P.nti + ti) * P.rows_global + n0 + my_col] =
+            (colacc[acc][0][my_col] + colacc[acc][1][my_col]) + (colacc[acc][2][my_col] + colacc[acc][3][my_col]);
+      {
+        float rp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a, b;
+          unpack2(rp2[j], a, b);
+          rp[j] = (a + b) * isig[j];
+        }
+        int r;
+        const float rsum = frag_row_sum(rp, lane, r);
+        if (wrow0 + r < P.rows_local)
+          P.row_part[(static_cast<size_t>(p) * P.ntj * 2 + tj * 2 + slice) * P.rows_local + wrow0 + r] = rsum;
+      }
+      if (slice_tid == 0 && slice == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur_r[j] = nxt_r[j];
+    }
+    if (STASH && slice_tid == 0) tma_store_wait_all<0>();
   }
   kernel_teardown<CG, EW>(tmem_base, warp);
 }
@@ -1085,6 +1430,254 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
   kernel_teardown<CG, EW>(tmem_base, warp);
 }
 
+// ============================================================================================== wide GEMM tiles
+// Gradient GEMMs (long k, narrow n): one 256 x wn tile per CTA pair, wn = 256 | 384 | 512 accumulator columns in a
+// single TMEM accumulator.  Per k block a CTA receives 16 KiB of A and wn * 64 bytes of B for 128 x wn x 64 MACs:
+// 157 (wn = 384) / 171 (wn = 512) flop per byte through the L2 -> SM fabric instead of 128 with the 256-column tiles,
+// which is what bounds the 256-column mainloop (measured: 43 B/clk/SM delivered, the chip-wide TMA ceiling).  With a
+// tile taking hundreds of k blocks the epilogue does not need a second accumulator to hide behind.
+//   B operands are MN-major only (xhat stored [sample][feature], k = sample).
+//   MMA 1 covers accumulator columns [0, 256): CTA r of the pair supplies columns 128 r .. 128 r + 127 (two boxes),
+//   MMA 2 covers columns [256, wn):            CTA r supplies (wn - 256) / 2 columns (one or two boxes).
+struct WideBarriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full;
+  uint64_t tmem_empty;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ Tile decode_wide(const GemmParams& P, int t) {
+  Tile r;
+  int j = 0;
+#pragma unroll
+  for (int u = 1; u < kMaxJobs; ++u)
+    if (u < P.njobs && t >= P.jobs[u].tile_base) j = u;
+  const Job& job = P.jobs[j];
+  const int local = t - job.tile_base;
+  const int tn = local % job.n_tiles;  // n fastest: the tiles sharing an A row panel run together
+  const int rest = local / job.n_tiles;
+  r.job = j;
+  r.split = rest % job.ksplits;
+  r.ti = rest / job.ksplits;
+  r.tj = tn;
+  r.m0 = r.ti * (2 * BM);
+  r.n0 = tn * P.wn;
+  return r;
+}
+
+// NP = 1: clusters of one CTA pair.  NP = 2 (jobs with exactly two n tiles): clusters of two pairs that work on the two
+// n tiles of the same 256 rows; every CTA loads one 64-row half of its A tile and multicasts it to the CTA of the other
+// pair that needs the same rows, so each A byte leaves L2 (and HBM) once per role and the pairs advance in lockstep.
+template <int EW, int NP>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid_constant__ GemmParams P) {
+  constexpr int S = EW / 4;
+  constexpr int CL = 2 * NP;  // CTAs per cluster
+  __shared__ WideBarriers bars;
+  uint8_t* smem = aligned_dyn_smem();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t half = rank & 1u;      // which 128 rows of the pair's 256
+  const uint32_t pair = rank >> 1;      // which n tile (NP == 2)
+  const uint32_t leader = rank & ~1u;   // CTA that issues this pair's MMAs
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  const int total = P.total_tiles / NP;  // NP == 2: one unit = both n tiles of (job, row tile, k split)
+  const int wn = P.wn;
+  const int n2 = wn - 256;                       // columns of the second MMA (0, 128 or 256)
+  const int stage_bytes = A_STAGE_BYTES + wn * 64;  // A 128 x 64 + B (wn / 2) x 64 fp16
+  const int stages = P.stages;
+
+  if (warp == EW && lane == 0) {
+    for (int i = 0; i < kMaxStages; ++i) {
+      mbar_init(&bars.full[i], 1);
+      mbar_init(&bars.empty[i], NP);  // one commit per pair whose loads write this CTA's slot
+    }
+    mbar_init(&bars.tmem_full, 1);
+    mbar_init(&bars.tmem_empty, 2 * EW);
+    fence_mbar_init();
+  }
+  if (warp == EW + 1) {
+    tmem_alloc<2>(&bars.tmem_base, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars.tmem_base);
+
+  auto decode = [&](int u) {
+    Tile t = decode_wide(P, NP == 1 ? u : 2 * u);
+    if (NP == 2) {
+      t.tj = static_cast<int>(pair);
+      t.n0 = t.tj * wn;
+    }
+    return t;
+  };
+
+  if (warp == EW) {
+    if (lane == 0) {
+      RingState rs;
+      const uint32_t full0 = mapa(smem_u32(&bars.full[0]), leader);
+      const uint16_t mc_mask = static_cast<uint16_t>(0b0101u << half);  // the CTAs holding the same 128 rows
+      for (int u = cluster_id; u < total; u += num_clusters) {
+        const Tile tile = decode(u);
+        const Job& job = P.jobs[tile.job];
+        const int m0 = tile.m0 + static_cast<int>(half) * BM;
+        const int nb1 = tile.n0 + static_cast<int>(half) * 128;             // this CTA's columns of MMA 1
+        const int nb2 = tile.n0 + 256 + static_cast<int>(half) * (n2 / 2);  // ... of MMA 2
+        for (int s = 0; s < job.nseg; ++s) {
+          const Segment seg = job.seg[s];
+          const CUtensorMap* ma = P.maps + seg.map_a;
+          const CUtensorMap* ma64 = P.maps + seg.map_a64;
+          const CUtensorMap* mb = P.maps + seg.map_b;
+          int kb_lo, kb_hi;
+          split_range(seg.num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            mbar_wait_bounded<NP == 2>(&bars.empty[rs.stage], rs.phase ^ 1u, 1);
+            uint8_t* sa = smem + rs.stage * stage_bytes;
+            uint8_t* sb = sa + A_STAGE_BYTES;
+            const int k = kb * BK;
+            const uint32_t bar = full0 + rs.stage * 8;
+            if (half == 0) mbar_expect_tx(&bars.full[rs.stage], 2 * stage_bytes);
+            if constexpr (NP == 1) {
+              if (!seg.a_mn) {
+                tma_load_2d_2sm(sa, ma, bar, k, m0);
+              } else {
+                tma_load_2d_2sm(sa, ma, bar, m0, k);
+                tma_load_2d_2sm(sa + MN_BOX_BYTES, ma, bar, m0 + 64, k);
+              }
+            } else {
+              // this CTA's 64-row share of the A tile, delivered to both CTAs that hold these 128 rows
+              uint8_t* dst = sa + pair * MN_BOX_BYTES;
+              const int mrow = m0 + static_cast<int>(pair) * 64;
+              if (!seg.a_mn) tma_load_2d_2sm_mc(dst, ma64, bar, k, mrow, mc_mask);
+              else tma_load_2d_2sm_mc(dst, ma, bar, mrow, k, mc_mask);
+            }
+            tma_load_2d_2sm(sb, mb, bar, nb1, k);
+            tma_load_2d_2sm(sb + MN_BOX_BYTES, mb, bar, nb1 + 64, k);
+            for (int g = 0; g < n2 / 128; ++g)
+              tma_load_2d_2sm(sb + (2 + g) * MN_BOX_BYTES, mb, bar, nb2 + g * 64, k);
+            rs.advance(stages);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == EW + 1) {
+    if (lane == 0 && half == 0) {
+      RingState rs;
+      int it = 0;
+      const uint16_t all_mask = NP == 2 ? 0b1111 : 0b11;
+      const uint16_t pair_mask = static_cast<uint16_t>(0b11u << (2 * pair));
+      for (int u = cluster_id; u < total; u += num_clusters, ++it) {
+        const Tile tile = decode(u);
+        const Job& job = P.jobs[tile.job];
+        mbar_wait_bounded<false>(&bars.tmem_empty, (it & 1) ^ 1u, 4);  // the epilogue has drained the accumulator
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int s = 0; s < job.nseg; ++s) {
+          const Segment seg = job.seg[s];
+          const uint32_t idesc1 = make_idesc_f16(2 * BM, 256, 0, seg.a_mn, 1);
+          const uint32_t idesc2 = make_idesc_f16(2 * BM, n2 > 0 ? n2 : 256, 0, seg.a_mn, 1);
+          int kb_lo, kb_hi;
+          split_range(seg.num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            mbar_wait_bounded<NP == 2>(&bars.full[rs.stage], rs.phase, 2);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + rs.stage * stage_bytes);
+            const uint32_t b_base = a_base + A_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = seg.a_mn ? make_smem_desc_sw128(a_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
+                                              : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t bdesc1 = make_smem_desc_sw128(b_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024);
+              umma_f16<2>(tmem_base, adesc, bdesc1, idesc1, accumulate);
+              if (n2 > 0) {
+                const uint64_t bdesc2 =
+                    make_smem_desc_sw128(b_base + 2 * MN_BOX_BYTES + k * (UMMA_K * 128), MN_BOX_BYTES, 1024);
+                umma_f16<2>(tmem_base + 256, adesc, bdesc2, idesc2, accumulate);
+              }
+              accumulate = 1;
+            }
+            umma_commit_2sm(&bars.empty[rs.stage], all_mask);  // frees the slot in every CTA whose loads fill it
+            rs.advance(stages);
+          }
+        }
+        umma_commit_2sm(&bars.tmem_full, pair_mask);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int slice = warp >> 2;
+    const int cs = wn / S;  // columns per slice (a multiple of 32)
+    float alpha = P.alpha0;
+    if (P.t3 != nullptr) {
+      float mx = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
+      alpha *= mx;
+    }
+    int it = 0;
+    for (int u = cluster_id; u < total; u += num_clusters, ++it) {
+      const Tile tile = decode(u);
+      const int j = tile.job;
+      const bool accumulate_out = P.jobs[j].ksplits > 1;
+      const int row = tile.m0 + static_cast<int>(half) * BM + q * 32 + lane;
+      const bool row_ok = row < P.m[j];
+      const int ncols = P.n[j];
+      const int c0 = tile.n0 + slice * cs;
+      float* out = P.out[j] + static_cast<size_t>(row) * P.ldc[j] + c0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slice * cs;
+      mbar_wait_bounded<false>(&bars.tmem_full, it & 1, 3);
+      tc_fence_after();
+      const int nch = cs / 32;
+      for (int ch = 0; ch < nch; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == nch - 1) {  // last TMEM read of this warp: hand the accumulator back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (half == 0) mbar_arrive(&bars.tmem_empty);
+            else mbar_arrive_cluster(&bars.tmem_empty, leader);
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const int col = c0 + ch * 32 + k4 * 4;
+            if (col + 3 < ncols) {
+              float4 o;
+              o.x = __uint_as_float(v[k4 * 4 + 0]) * alpha;
+              o.y = __uint_as_float(v[k4 * 4 + 1]) * alpha;
+              o.z = __uint_as_float(v[k4 * 4 + 2]) * alpha;
+              o.w = __uint_as_float(v[k4 * 4 + 3]) * alpha;
+              float* dst = out + ch * 32 + k4 * 4;
+              if (!accumulate_out) *reinterpret_cast<float4*>(dst) = o;
+              else red_add_v4(dst, o);  // k-split partial sums are combined by fp32 adds in L2
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();  // no CTA of the cluster may exit while another can still signal its barriers
+  if (warp == EW + 1) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host launchers
 int sm_count() {
   static int cached = 0;
@@ -1142,10 +1735,22 @@ int tile_smem_bytes(int cg, int stages, int slabs) {
   return stages * stage_bytes + slabs * kSlabBytes + 1024;
 }
 
-int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream) {
+int launch_forward_tiles(const FwdParams& p0, int cg, int ew, cudaStream_t stream) {
+  FwdParams p = p0;
   const int smem = tile_smem_bytes(cg, p.stages, p.stash ? 4 : 0);
   const int total = p.npairs * (p.nti / cg) * p.tj_count;
   if (total <= 0) return SCLIP_OK;
+  static const bool fast_on = [] {
+    const char* e = getenv("SCLIP_FAST");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (cg == 2 && fast_on) {
+    // pairs with s < kFoldMaxScale (decided on the device: the scales are never read by the host), then the rest
+    const int rc = p.stash ? launch_persistent(forward_fast_kernel<true>, p, 2, 8, smem, total, stream)
+                           : launch_persistent(forward_fast_kernel<false>, p, 2, 8, smem, total, stream);
+    if (rc) return rc;
+    p.pair_filter = 1;
+  }
   SCLIP_DISPATCH(forward_tiles_kernel, smem, total, stream);
 }
 
@@ -1160,6 +1765,35 @@ int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream) {
   const int total = p.total_tiles;
   if (total <= 0) return SCLIP_OK;
   SCLIP_DISPATCH(gemm_tiles_kernel, smem, total, stream);
+}
+
+int wide_stages(int wn) {
+  const int st = (227 * 1024 - 2048) / (A_STAGE_BYTES + wn * 64);
+  return st > kMaxStages ? kMaxStages : st;
+}
+
+int launch_gemm_wide(const GemmParams& p, int ew, cudaStream_t stream) {
+  if (p.total_tiles <= 0) return SCLIP_OK;
+  if (p.wn != 256 && p.wn != 384 && p.wn != 512) {
+    set_error("internal: wide GEMM tile width %d", p.wn);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const int smem = p.stages * (A_STAGE_BYTES + p.wn * 64) + 1024;
+  // SCLIP_MCAST=1 (experiment, off by default): two pairs per cluster share the A tiles by TMA multicast when every
+  // job has exactly two n tiles.  Measured on B200 (32768 x 768 x 32768): 850 TFLOP/s against 1355 TFLOP/s for
+  // independent pairs -- the lockstep of four CTAs costs more than the 20 % of L2 reads it saves.
+  static const bool mcast_on = [] {
+    const char* e = getenv("SCLIP_MCAST");
+    return e != nullptr && e[0] == '1';
+  }();
+  bool two = mcast_on && p.total_tiles % 2 == 0;
+  for (int j = 0; j < p.njobs; ++j) two = two && p.jobs[j].n_tiles == 2;
+  if (two) {
+    if (ew == 16) return launch_persistent(gemm_wide_kernel<16, 2>, p, 4, 16, smem, p.total_tiles / 2, stream);
+    return launch_persistent(gemm_wide_kernel<8, 2>, p, 4, 8, smem, p.total_tiles / 2, stream);
+  }
+  if (ew == 16) return launch_persistent(gemm_wide_kernel<16, 1>, p, 2, 16, smem, p.total_tiles, stream);
+  return launch_persistent(gemm_wide_kernel<8, 1>, p, 2, 8, smem, p.total_tiles, stream);
 }
 
 }  // namespace sclip

@@ -80,7 +80,7 @@ class EmulatedBackend:
         lay = ws.lay
         if tile_hi <= tile_lo:
             return
-        row_part = ws.view(lay.row_part, (3, lay.col_tiles, bl), torch.float32)
+        row_part = ws.view(lay.row_part, (3, 2 * lay.col_tiles, bl), torch.float32)
         col_part = ws.view(lay.col_part, (3, lay.row_tiles, bg), torch.float32)
         tile_ref = ws.view(lay.tile_ref, (3, lay.row_tiles, lay.col_tiles), torch.float32)
         diag = ws.view(lay.diag, (3, bl), torch.float32)
@@ -93,8 +93,8 @@ class EmulatedBackend:
             ref = 0.0 if math.exp(float(t3[p])) < 64.0 else float(math.exp(float(t3[p])))
             tile_ref[p] = ref
             e = torch.exp(logits[:, c0:c1] - ref)
-            row_part[p, tile_lo + 1:tile_hi] = 0.0
-            row_part[p, tile_lo] = e.sum(1).float()
+            row_part[p, 2 * tile_lo + 1:2 * tile_hi] = 0.0
+            row_part[p, 2 * tile_lo] = e.sum(1).float()
             col_part[p, :, c0:c1] = 0.0
             col_part[p, 0, c0:c1] = e.sum(0).float()
             if c0 <= off < c1:
@@ -107,7 +107,7 @@ class EmulatedBackend:
     def forward_reduce(self, ws):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
-        row_part = ws.view(lay.row_part, (3, lay.col_tiles, bl), torch.float32).double()
+        row_part = ws.view(lay.row_part, (3, 2 * lay.col_tiles, bl), torch.float32).double()
         col_part = ws.view(lay.col_part, (3, lay.row_tiles, bg), torch.float32).double()
         ref = ws.view(lay.tile_ref, (3, lay.row_tiles, lay.col_tiles), torch.float32).double()[:, 0, 0]
         rsum, csum = row_part.sum(1), col_part.sum(1)

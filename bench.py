@@ -221,7 +221,19 @@ def stage_breakdown(run, steps):
             if name in ("begin", "backward_begin"):
                 continue
             acc.setdefault(name, []).append(a.elapsed_time(b))
-    return {k: sum(v) / len(v) for k, v in acc.items()}
+    avg = {k: sum(v) / len(v) for k, v in acc.items()}
+    # the sharded path marks sub-stages (tile waves, the two GEMM roles, the statistics exchange): fold them into the
+    # six stage names, keeping the detail under "<stage>/<sub>"
+    folds = {"forward_tiles_local": "forward_tiles", "forward_tiles_wave1": "forward_tiles",
+             "forward_reduce": "forward_finish", "forward_barrier1": "forward_finish",
+             "backward_gemms_col": "backward_gemms", "backward_gemms_row": "backward_gemms"}
+    out = {}
+    for k, v in avg.items():
+        tgt = "forward_tiles" if k.startswith("forward_tiles_") else folds.get(k, k)
+        out[tgt] = out.get(tgt, 0.0) + v
+        if tgt != k:
+            out[f"{tgt}/{k}"] = v
+    return out
 
 
 def main():

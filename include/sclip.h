@@ -127,6 +127,9 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
  * tiles into grad_tiles, so that the backward needs no recomputation of the similarities (sclip_backward_scale
  * instead of sclip_backward_tiles).  Needs diag_all (sclip_forward_diag, all-gathered when world > 1). */
 #define SCLIP_FWD_STASH 1
+/* flags & SCLIP_FWD_WRAP: the column tiles [col_tile_begin, col_tile_end) are taken modulo col_tiles (a range of
+ * ranks' columns that wraps around the end of the global batch); col_tile_end - col_tile_begin <= col_tiles. */
+#define SCLIP_FWD_WRAP 2
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
                              int col_tile_begin, int col_tile_end, int flags, void* stream);
 
@@ -190,6 +193,31 @@ int sclip_set_max_sms(int max_sms);
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                           const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,
                           void* dtxt, void* daud, int out_f32, int flags, float* dt3, void* stream);
+
+/* ---- peer-memory exchanges (world > 1) ------------------------------------------------------------
+ * When every rank's workspace lives in symmetric memory (mapped into all processes of the node over NVLink /
+ * NVSwitch), the exchanges the reference would do with torch.distributed collectives are kernels of this library that
+ * load straight from the peers' workspaces.  peer_ws[r] is the base of rank r's workspace in this process' address
+ * space (peer_ws[rank] == ws), world <= SCLIP_MAX_PEERS.  The caller orders the ranks (a signal-pad / flag barrier on
+ * the same stream before each call: the sources must be complete and must not be rewritten while peers read). */
+#define SCLIP_MAX_PEERS 16
+
+/* Pull all-gather: copy the normalised operand shards (and their positive-pair logits) of the `count` ranks
+ * (rank + first + i) % world, i in [0, count), into this rank's xhat / diag_all.  At most max_blocks thread blocks. */
+int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
+                      int max_blocks, void* stream);
+
+/* col_lse_all[r][3][rows_global] = rank r's lse_col_local (the input of sclip_forward_loss). */
+int sclip_pull_col_lse(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* col_lse_all,
+                       void* stream);
+
+/* loss3[p] = sum over ranks of loss_part[p]: every rank ends up with the global-batch losses. */
+int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3, void* stream);
+
+/* Pull reduce-scatter: col_contrib[m][i][:] = sum over ranks r (rank order) of rank r's dxhat_col[m][row_offset + i][:]
+ * -- the column-role gradients of this rank's rows, ready for sclip_backward_finish. */
+int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* const* peer_ws, int max_blocks,
+                           void* stream);
 
 /* ---- single-GPU convenience (world == 1): the whole tail in two calls ---------------------------
  * keep_for_backward != 0: sclip_backward will follow on the same workspace (SCLIP_MATH_F16 then stashes in the

@@ -187,6 +187,12 @@ int launch_backward_finish(const Workspace& w, const void* const x3[3], const fl
                            const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, int stash,
                            float* dt3, cudaStream_t stream);
 int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream);
+// peer-memory exchanges (world > 1, workspaces in symmetric memory); peer_ws[r] = base of rank r's workspace
+int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
+                       cudaStream_t stream);
+int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, cudaStream_t stream);
+int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t src_off, int count, float* out,
+                      bool sum_loss, cudaStream_t stream);
 int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, bool factors_only, cudaStream_t stream);
 
 }  // namespace sclip

@@ -430,8 +430,10 @@ int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float
     set_error("t3 is null");
     return SCLIP_ERR_ARGUMENT;
   }
-  if (col_tile_end > w.lay.col_tiles) col_tile_end = w.lay.col_tiles;
-  if (col_tile_begin < 0 || col_tile_begin > col_tile_end) {
+  const bool wrap = (flags & SCLIP_FWD_WRAP) != 0;
+  if (!wrap && col_tile_end > w.lay.col_tiles) col_tile_end = w.lay.col_tiles;
+  if (col_tile_begin < 0 || col_tile_begin > col_tile_end || col_tile_begin >= w.lay.col_tiles + (wrap ? 0 : 1) ||
+      col_tile_end - col_tile_begin > w.lay.col_tiles) {
     set_error("bad column tile range [%d, %d)", col_tile_begin, col_tile_end);
     return SCLIP_ERR_ARGUMENT;
   }
@@ -687,6 +689,81 @@ int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* im
   }
   return launch_backward_finish(w, x3, t3, g3, col_contrib, grad_mult, dx3, out_f32, (flags & SCLIP_BWD_STASHED) ? 1 : 0,
                                 dt3, static_cast<cudaStream_t>(stream));
+}
+
+static int check_peers(const Workspace& w, void* ws, const void* const* peer_ws) {
+  if (w.pb.world < 2 || w.pb.world > SCLIP_MAX_PEERS || peer_ws == nullptr) {
+    set_error("peer-memory calls need 2 <= world <= %d and a peer workspace table", SCLIP_MAX_PEERS);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (w.pb.rows_local * w.pb.world != w.pb.rows_global || w.pb.row_offset % w.pb.rows_local != 0) {
+    set_error("peer-memory calls need equal row shards (rows_global = world * rows_local)");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const int rank = w.pb.row_offset / w.pb.rows_local;
+  for (int r = 0; r < w.pb.world; ++r)
+    if (peer_ws[r] == nullptr || (reinterpret_cast<uintptr_t>(peer_ws[r]) & 255u) != 0) {
+      set_error("peer workspace %d is null or not 256-byte aligned", r);
+      return SCLIP_ERR_ARGUMENT;
+    }
+  if (peer_ws[rank] != ws) {
+    set_error("peer_ws[rank] must be this rank's own workspace");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return SCLIP_OK;
+}
+
+int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
+                      int max_blocks, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (!rc) rc = check_peers(w, ws, peer_ws);
+  if (rc) return rc;
+  if (first < 1 || count < 0 || first + count > w.pb.world) {
+    set_error("bad peer range first=%d count=%d (world %d)", first, count, w.pb.world);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  if (count == 0) return SCLIP_OK;
+  return launch_pull_shards(w, peer_ws, first, count, max_blocks, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_pull_col_lse(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* col_lse_all,
+                       void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (!rc) rc = check_peers(w, ws, peer_ws);
+  if (rc) return rc;
+  if (col_lse_all == nullptr) {
+    set_error("col_lse_all is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_pull_stats(w, peer_ws, w.lay.lse_col_local, 3 * w.pb.rows_global, col_lse_all, false,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (!rc) rc = check_peers(w, ws, peer_ws);
+  if (rc) return rc;
+  if (loss3 == nullptr) {
+    set_error("loss3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_pull_stats(w, peer_ws, w.lay.loss_part, 3, loss3, true, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* const* peer_ws, int max_blocks,
+                           void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (!rc) rc = check_peers(w, ws, peer_ws);
+  if (rc) return rc;
+  if (w.pb.dim % 4 != 0) {
+    set_error("dim must be a multiple of 4");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_pull_reduce(w, peer_ws, max_blocks, static_cast<cudaStream_t>(stream));
 }
 
 // the single-GPU convenience calls remember, per workspace, whether the last forward stashed

@@ -1,6 +1,8 @@
 // HBM-bound SIMT kernels around the tensor-core tiles: the fused normalise + cast prologue
 // (model.py:248-250), the merge of per-tile softmax statistics into log-sum-exps and the three
 // losses (model.py:52-58), and the backward of the normalisation plus dL/dlogit_scale.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace sclip {
@@ -483,6 +485,126 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ peer memory
+// world > 1 with the workspaces in symmetric memory (every rank's blob mapped into every process over NVLink /
+// NVSwitch): the exchanges are plain kernels that load straight from the peers' workspaces -- a pull all-gather of
+// the operand shards, a pull reduce(-scatter) of the column-role gradient partial sums, and gathers of the small
+// per-column / per-rank statistics.  One NVSwitch hop per byte; ordering between ranks comes from the host's
+// signal-pad barriers on the same stream.
+__device__ __forceinline__ uint4 ld_peer(const uint4* p) { return __ldcg(p); }  // L2 only: never a stale L1 line
+
+struct PullShardArgs {
+  const uint8_t* peer[SCLIP_MAX_PEERS];   // workspace bases of the selected source ranks
+  int peer_rank[SCLIP_MAX_PEERS];
+  uint8_t* local;
+  unsigned long long xhat_off, xhat_lo_off, diag_off;
+  int nseg;  // 3, or 6 with the low halves
+  int rows_local, rows_global, dim;
+};
+
+__global__ void __launch_bounds__(1024) pull_shards_kernel(const PullShardArgs a) {
+  const int pi = blockIdx.y;
+  const uint8_t* src = a.peer[pi];
+  const size_t row0 = static_cast<size_t>(a.peer_rank[pi]) * a.rows_local;
+  const size_t seg_units = static_cast<size_t>(a.rows_local) * a.dim * 2 / 16;  // 16-byte units per modality shard
+  const size_t total = a.nseg * seg_units;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  auto locate = [&](size_t u) {
+    const int sg = static_cast<int>(u / seg_units);
+    const size_t w = u - sg * seg_units;
+    return (sg < 3 ? a.xhat_off : a.xhat_lo_off) + ((static_cast<size_t>(sg % 3) * a.rows_global + row0) * a.dim) * 2 +
+           w * 16;
+  };
+  size_t u = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; u + 3 * stride < total; u += 4 * stride) {  // four independent 16-byte loads in flight per thread
+    size_t o[4];
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = locate(u + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ld_peer(reinterpret_cast<const uint4*>(src + o[k]));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(a.local + o[k]) = v[k];
+  }
+  for (; u < total; u += stride) {
+    const size_t o = locate(u);
+    *reinterpret_cast<uint4*>(a.local + o) = ld_peer(reinterpret_cast<const uint4*>(src + o));
+  }
+  // positive-pair logits of the peer's rows (stash scaling)
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3u * a.rows_local; i += stride) {
+    const size_t p = i / a.rows_local, r = i - p * a.rows_local;
+    const size_t o = a.diag_off + (p * a.rows_global + row0 + r) * 4;
+    *reinterpret_cast<float*>(a.local + o) = __ldcg(reinterpret_cast<const float*>(src + o));
+  }
+}
+
+struct PullReduceArgs {
+  const uint8_t* peer[SCLIP_MAX_PEERS];  // all ranks in rank order (this rank included)
+  int world;
+  unsigned long long src_off;   // dxhat_col: [3][rows_global][dim] fp32 in every workspace
+  float* out;                   // col_contrib: [3][rows_local][dim] fp32
+  int rows_local, rows_global, row_offset, dim;
+};
+
+// out[m][i][:] = sum over ranks r (in rank order: deterministic) of dxhat_col_r[m][row_offset + i][:]
+template <int W>
+__global__ void __launch_bounds__(512) pull_reduce_kernel(const PullReduceArgs a) {
+  const size_t per_m = static_cast<size_t>(a.rows_local) * a.dim / 4;  // float4 units per modality
+  const size_t total = 3 * per_m;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int world = W > 0 ? W : a.world;
+  for (size_t u = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; u < total; u += stride) {
+    const size_t m = u / per_m, w = u - m * per_m;
+    const size_t o = a.src_off + ((m * a.rows_global + a.row_offset) * a.dim) * 4 + w * 16;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (W > 0) {
+      uint4 v[W];
+#pragma unroll
+      for (int r = 0; r < W; ++r) v[r] = ld_peer(reinterpret_cast<const uint4*>(a.peer[r] + o));
+#pragma unroll
+      for (int r = 0; r < W; ++r) {
+        acc.x += __uint_as_float(v[r].x);
+        acc.y += __uint_as_float(v[r].y);
+        acc.z += __uint_as_float(v[r].z);
+        acc.w += __uint_as_float(v[r].w);
+      }
+    } else {
+      for (int r = 0; r < world; ++r) {
+        const uint4 v = ld_peer(reinterpret_cast<const uint4*>(a.peer[r] + o));
+        acc.x += __uint_as_float(v.x);
+        acc.y += __uint_as_float(v.y);
+        acc.z += __uint_as_float(v.z);
+        acc.w += __uint_as_float(v.w);
+      }
+    }
+    reinterpret_cast<float4*>(a.out)[u] = acc;
+  }
+}
+
+struct PullStatsArgs {
+  const uint8_t* peer[SCLIP_MAX_PEERS];  // all ranks in rank order
+  int world;
+  unsigned long long src_off;  // float array at this offset of every workspace
+  float* out;                  // [world][count]
+  int count;
+};
+
+__global__ void __launch_bounds__(256) pull_stats_kernel(const PullStatsArgs a) {
+  const int r = blockIdx.y;
+  const float* src = reinterpret_cast<const float*>(a.peer[r] + a.src_off);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += gridDim.x * blockDim.x)
+    a.out[static_cast<size_t>(r) * a.count + i] = __ldcg(src + i);
+}
+
+// loss3[p] = sum over ranks of loss_part_r[p]
+__global__ void pull_loss_kernel(const PullStatsArgs a) {
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int r = 0; r < a.world; ++r) s += __ldcg(reinterpret_cast<const float*>(a.peer[r] + a.src_off) + threadIdx.x);
+    a.out[threadIdx.x] = s;
+  }
+}
+
 }  // namespace
 
 int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream) {
@@ -589,6 +711,72 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
   ScaleArgs a{w.g[0], w.fac_row, w.fac_col, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col};
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);
   backward_scale_kernel<<<grid, 256, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+}  // namespace sclip
+
+namespace sclip {
+
+int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
+                       cudaStream_t stream) {
+  PullShardArgs a;
+  memset(&a, 0, sizeof(a));
+  const int world = w.pb.world, rank = w.pb.row_offset / w.pb.rows_local;
+  for (int i = 0; i < count; ++i) {
+    const int r = (rank + first + i) % world;
+    a.peer[i] = static_cast<const uint8_t*>(peer_ws[r]);
+    a.peer_rank[i] = r;
+  }
+  a.local = w.base;
+  a.xhat_off = w.lay.xhat;
+  a.xhat_lo_off = w.lay.xhat_lo;
+  a.diag_off = w.lay.diag_all;
+  a.nseg = w.pb.math == SCLIP_MATH_F16X3 ? 6 : 3;
+  a.rows_local = w.pb.rows_local;
+  a.rows_global = w.pb.rows_global;
+  a.dim = w.pb.dim;
+  int bx = max_blocks / count;
+  if (bx < 1) bx = 1;
+  pull_shards_kernel<<<dim3(bx, count), 1024, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, cudaStream_t stream) {
+  PullReduceArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int r = 0; r < w.pb.world; ++r) a.peer[r] = static_cast<const uint8_t*>(peer_ws[r]);
+  a.world = w.pb.world;
+  a.src_off = w.lay.dxhat_col;
+  a.out = reinterpret_cast<float*>(w.base + w.lay.col_contrib);
+  a.rows_local = w.pb.rows_local;
+  a.rows_global = w.pb.rows_global;
+  a.row_offset = w.pb.row_offset;
+  a.dim = w.pb.dim;
+  const int blocks = max_blocks < 1 ? 1 : max_blocks;
+  switch (w.pb.world) {
+    case 2: pull_reduce_kernel<2><<<blocks, 512, 0, stream>>>(a); break;
+    case 4: pull_reduce_kernel<4><<<blocks, 512, 0, stream>>>(a); break;
+    case 8: pull_reduce_kernel<8><<<blocks, 512, 0, stream>>>(a); break;
+    default: pull_reduce_kernel<0><<<blocks, 512, 0, stream>>>(a); break;
+  }
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
+int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t src_off, int count, float* out,
+                      bool sum_loss, cudaStream_t stream) {
+  PullStatsArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int r = 0; r < w.pb.world; ++r) a.peer[r] = static_cast<const uint8_t*>(peer_ws[r]);
+  a.world = w.pb.world;
+  a.src_off = src_off;
+  a.out = out;
+  a.count = count;
+  if (sum_loss) pull_loss_kernel<<<1, 32, 0, stream>>>(a);
+  else pull_stats_kernel<<<dim3((count + 1023) / 1024 > 32 ? 32 : (count + 1023) / 1024, w.pb.world), 256, 0, stream>>>(a);
   SCLIP_CUDA_OK(cudaGetLastError());
   return SCLIP_OK;
 }

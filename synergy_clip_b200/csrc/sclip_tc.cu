@@ -392,13 +392,16 @@ __device__ __forceinline__ int select_pairs(const FwdParams& P, bool fast, int (
   return n;
 }
 
+// ntj_wrap > 0: the column tiles [tj_begin, tj_begin + ntj) are taken modulo ntj_wrap (a range of ranks' columns that
+// wraps around the end of the global batch)
 template <int CG>
-__device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int tj_begin = 0) {
+__device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int tj_begin = 0, int ntj_wrap = 0) {
   Tile r;
   const int per_pair = nti_c * ntj;
   r.job = t / per_pair;
   decode_grouped(t - r.job * per_pair, nti_c, ntj, r.ti, r.tj);
   r.tj += tj_begin;
+  if (ntj_wrap > 0 && r.tj >= ntj_wrap) r.tj -= ntj_wrap;
   r.m0 = r.ti * Geo<CG>::kTileM;
   r.n0 = r.tj * BN;
   r.split = 0;
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
     if (lane == 0) {
       RingState rs;
       for (int t = cluster_id; t < total; t += num_clusters) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
         tile.job = pairs[tile.job];
         producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
       }
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
         tile.job = pairs[tile.job];
         const int acc = it & 1;
         mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
     };
     int it = 0;
     for (int t = cluster_id; t < total; t += num_clusters, ++it) {
-      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
       tile.job = pairs[tile.job];
       const int acc = it & 1;
       const int p = tile.job;
@@ -657,7 +660,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
       release_accumulator<CG>(&bars, acc, rank, lane);  // all TMEM reads of this warp are complete
       pre_valid = false;
       if (P.stash && t + num_clusters < total) {  // start the next tile's diagonal loads under this tile's tail
-        Tile nx = decode_similarity<CG>(t + num_clusters, nti_c, P.tj_count, P.tj_begin);
+        Tile nx = decode_similarity<CG>(t + num_clusters, nti_c, P.tj_count, P.tj_begin, P.ntj);
         const int np = pairs[nx.job];
         load_diag(np, (nx.ti * CG + static_cast<int>(rank)) * BM + q * 32, nx.n0, pre_r, pre_c);
         pre_valid = true;
@@ -754,7 +757,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
     if (lane == 0) {
       RingState rs;
       for (int t = cluster_id; t < total; t += num_clusters) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
         tile.job = pairs[tile.job];
         producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
       }
@@ -765,7 +768,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
         tile.job = pairs[tile.job];
         const int acc = it & 1;
         mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
@@ -786,7 +789,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
 
     // positive-pair logits of a tile's rows / columns -> stash factors (loaded one tile ahead)
     auto tile_coords = [&](int t, int& p, int& ti, int& tj, int& m0, int& n0) {
-      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin);
+      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
       p = pairs[tile.job];
       ti = tile.ti * CG + static_cast<int>(rank);
       tj = tile.tj;
@@ -840,12 +843,13 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
 
       mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
       tc_fence_after();
-      if (P.debug != 0) {  // profiling experiments: 1 = mainloop without the epilogue, 2 / 3 = only the TMEM loads
-        if (P.debug >= 2) {    //                        (2: 16x256b fragments, 3: 32x32b rows)
+      const bool dbg_nostore = (P.debug & 16) != 0, dbg_nostage = (P.debug & 32) != 0, dbg_nostat = (P.debug & 64) != 0;
+      if ((P.debug & 15) != 0) {  // profiling experiments: 1 = mainloop without the epilogue, 2 / 3 = only the TMEM loads
+        if ((P.debug & 15) >= 2) {  //                     (2: 16x256b fragments, 3: 32x32b rows)
           uint32_t v[32];
           uint32_t sink = 0;
           for (int ch = 0; ch < NCH; ++ch) {
-            if (P.debug == 2) tmem_ld_block32(taddr + ch * 32, v);
+            if ((P.debug & 15) == 2) tmem_ld_block32(taddr + ch * 32, v);
             else tmem_ld_32x32b_x32(taddr + ch * 32, v);
             tmem_ld_wait();
 #pragma unroll
@@ -915,7 +919,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
             const uint64_t b = fadd2(e2[8 * g + 4 + h], e2[8 * g + 6 + h]);
             rp2[2 * g + h] = fadd2(rp2[2 * g + h], fadd2(a, b));
           }
-        if constexpr (STASH) {
+        if (STASH && !dbg_nostage) {
           // E~ = e' tau_j, packed to fp16 and staged through stmatrix in the TMA store's swizzled layout
           uint8_t* slab = staging + (slice * 2 + (ch >> 1)) * kSlabBytes;
           const uint32_t slab_addr = smem_u32(slab) + st_row + ((ch & 1) ? st_chunk1 : st_chunk0);
@@ -979,7 +983,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
           if constexpr (STASH) {
             if (slice_tid == 0) {
               const int gcol = n0 + col0 + (ch >> 1) * 64;
-              if (gcol < P.rows_global)
+              if (gcol < P.rows_global && !dbg_nostore)
                 tma_store_2d(&P.maps[P.store_map[p]], staging + (slice * 2 + (ch >> 1)) * kSlabBytes, gcol, m0);
               tma_store_commit();
             }
@@ -987,7 +991,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
         }
       }
       // column statistics of this slice: the four lane quarters are complete after the last slab barrier
-      if (n0 + my_col < P.rows_global)
+      if (n0 + my_col < P.rows_global && !dbg_nostat)
         P.col_part[(static_cast<size_t>(p) * P.nti + ti) * P.rows_global + n0 + my_col] =
             (colacc[acc][0][my_col] + colacc[acc][1][my_col]) + (colacc[acc][2][my_col] + colacc[acc][3][my_col]);
       {
@@ -1000,7 +1004,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
         }
         int r;
         const float rsum = frag_row_sum(rp, lane, r);
-        if (wrow0 + r < P.rows_local)
+        if (wrow0 + r < P.rows_local && !dbg_nostat)
           P.row_part[(static_cast<size_t>(p) * P.ntj * 2 + tj * 2 + slice) * P.rows_local + wrow0 + r] = rsum;
       }
       if (slice_tid == 0 && slice == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = 0.f;

@@ -13,6 +13,7 @@ no CPU or eager fallback, and a missing library or a failed call raises.
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 from ctypes import byref
 from typing import Optional, Tuple
@@ -43,7 +44,8 @@ class TriContrastiveConfig:
     """
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
-                 overlap: bool = True, comm_sms: int = 20, stash="auto", fuse_scale: bool = False):
+                 overlap: bool = True, comm_sms: int = 20, stash="auto", fuse_scale: bool = False,
+                 transport: str = "auto"):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -66,6 +68,16 @@ class TriContrastiveConfig:
         # shared-memory bandwidth (TMA writes + tensor-core reads ~ 125 B/clk/SM), which the conversion's extra
         # read + write of every A tile exceeds.
         self.fuse_scale = fuse_scale
+        # world_size > 1: how the shards move between ranks.
+        #   "p2p"  -- the workspace lives in symmetric memory (torch.distributed._symmetric_memory: every rank's blob
+        #             mapped into every process over NVLink / NVSwitch) and the exchanges are kernels of the library
+        #             that load straight from the peers' workspaces (pull all-gather of the operand shards in two waves
+        #             under the tiles, pull reduce of the column-role gradients under the row-role GEMMs);
+        #   "nccl" -- torch.distributed collectives (all-gather / reduce-scatter) on a side stream;
+        #   "auto" -- "p2p" on CUDA when symmetric memory is available, else "nccl".
+        if transport not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"transport={transport!r}")
+        self.transport = transport
 
 
 _DEFAULT = TriContrastiveConfig()
@@ -80,6 +92,7 @@ def _mark(name: str) -> None:
 
 
 _COMM_STREAMS = {}
+_LAST_COMM_EVENTS = None  # probe only: (name, event) pairs of the side stream during a traced step
 
 
 def _all_gather(pieces, group, coalesce):
@@ -148,6 +161,46 @@ class _Workspace:
         return ctypes.c_void_p(self.blob.data_ptr())
 
 
+class _SymmWorkspace(_Workspace):
+    """Workspace blob in symmetric memory: `peer_ptrs[r]` is rank r's blob in this process' address space.
+    Construction is a collective over the process group (every rank creates its workspaces in the same order)."""
+
+    def __init__(self, pb: Problem, device: torch.device, group):
+        import torch.distributed._symmetric_memory as symm
+
+        self.pb = pb
+        self.lay = _lib.plan(pb)
+        nbytes = int(self.lay.total_bytes)
+        raw = symm.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        if raw.data_ptr() % 256 != 0:
+            raise _lib.SclipError("symmetric-memory allocation is not 256-byte aligned")
+        self.hdl = symm.rendezvous(raw, group)
+        self._raw = raw
+        self.blob = raw[:nbytes]
+        ptrs = list(self.hdl.buffer_ptrs)
+        self.peer_ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
+        self.group = group
+
+
+def _symm_available() -> bool:
+    try:
+        import torch.distributed._symmetric_memory as symm  # noqa: F401
+
+        return hasattr(symm, "empty") and hasattr(symm, "rendezvous")
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def _use_p2p(cfg, img) -> bool:
+    if cfg.process_group is None or not img.is_cuda or _BACKEND.allows_cpu:
+        return False
+    if cfg.transport == "nccl":
+        return False
+    if cfg.transport == "p2p":
+        return True
+    return _symm_available()
+
+
 class _Pool:
     """Workspaces are recycled per problem shape; one is held from forward until its backward has run."""
 
@@ -156,19 +209,22 @@ class _Pool:
         self._lock = threading.Lock()
 
     @staticmethod
-    def _key(pb: Problem, device):
-        return (device.index, pb.rows_local, pb.rows_global, pb.row_offset, pb.dim, pb.dtype, pb.math, pb.world)
+    def _key(pb: Problem, device, symm_group=None):
+        return (device.index, pb.rows_local, pb.rows_global, pb.row_offset, pb.dim, pb.dtype, pb.math, pb.world,
+                None if symm_group is None else id(symm_group))
 
-    def acquire(self, pb: Problem, device) -> _Workspace:
+    def acquire(self, pb: Problem, device, symm_group=None) -> _Workspace:
         with self._lock:
-            lst = self._free.get(self._key(pb, device))
+            lst = self._free.get(self._key(pb, device, symm_group))
             if lst:
                 return lst.pop()
+        if symm_group is not None:
+            return _SymmWorkspace(pb, device, symm_group)
         return _Workspace(pb, device)
 
     def release(self, ws: _Workspace):
         with self._lock:
-            self._free.setdefault(self._key(ws.pb, ws.blob.device), []).append(ws)
+            self._free.setdefault(self._key(ws.pb, ws.blob.device, getattr(ws, "group", None)), []).append(ws)
 
     def clear(self):
         with self._lock:
@@ -253,9 +309,10 @@ class _CudaBackend:
     def forward_tiles(self, ws, t3):
         _lib.check(self.lib.sclip_forward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_tiles")
 
-    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False):
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False, wrap=False):
         _lib.check(self.lib.sclip_forward_tiles_cols(byref(ws.pb), ws.ptr, _ptr(t3), int(pair_mask), int(tile_lo),
-                                                     int(tile_hi), 1 if stash else 0, _stream()),
+                                                     int(tile_hi), (1 if stash else 0) | (2 if wrap else 0),
+                                                     _stream()),
                    "sclip_forward_tiles_cols")
 
     def forward_diag(self, ws, t3):
@@ -275,6 +332,22 @@ class _CudaBackend:
 
     def set_max_sms(self, n):
         return self.lib.sclip_set_max_sms(int(n))
+
+    def pull_shards(self, ws, first, count, max_blocks):
+        _lib.check(self.lib.sclip_pull_shards(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(first), int(count),
+                                              int(max_blocks), _stream()), "sclip_pull_shards")
+
+    def pull_col_lse(self, ws, col_all):
+        _lib.check(self.lib.sclip_pull_col_lse(byref(ws.pb), ws.ptr, ws.peer_ptrs, _ptr(col_all), _stream()),
+                   "sclip_pull_col_lse")
+
+    def pull_loss(self, ws, loss3):
+        _lib.check(self.lib.sclip_pull_loss(byref(ws.pb), ws.ptr, ws.peer_ptrs, _ptr(loss3), _stream()),
+                   "sclip_pull_loss")
+
+    def pull_reduce_cols(self, ws, max_blocks):
+        _lib.check(self.lib.sclip_pull_reduce_cols(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(max_blocks), _stream()),
+                   "sclip_pull_reduce_cols")
 
     def forward_reduce(self, ws):
         _lib.check(self.lib.sclip_forward_reduce(byref(ws.pb), ws.ptr, _stream()), "sclip_forward_reduce")
@@ -324,6 +397,8 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
         be.forward_loss(ws, None, loss3)
         _mark("forward_finish")
         return loss3
+    if isinstance(ws, _SymmWorkspace):
+        return _forward_p2p(ws, t3, cfg, stash, loss3)
     import torch.distributed as dist
 
     pg = cfg.process_group
@@ -379,6 +454,85 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
     return loss3
 
 
+def _forward_p2p(ws: "_SymmWorkspace", t3, cfg: TriContrastiveConfig, stash: bool, loss3: torch.Tensor):
+    """world > 1, workspace in symmetric memory.  After the prologue the operand shards of the other ranks are pulled
+    over NVLink by `sclip_pull_shards` in two waves on the side stream while the tiles of the columns already present
+    run: own columns, then the first wave's, then the second wave's.  Barriers are the symmetric-memory signal pads
+    (channel 0 on the side stream, 1 and 2 on the compute stream)."""
+    be = _BACKEND
+    pb, lay, hdl = ws.pb, ws.lay, ws.hdl
+    bl, off, world = pb.rows_local, pb.row_offset, pb.world
+    dev = ws.blob.device
+    cur = torch.cuda.current_stream()
+    comm = _comm_stream(dev)
+    tiles_per_rank = bl // 256
+    pipelined = cfg.overlap and bl % 256 == 0
+    blocks = 2 * max(cfg.comm_sms, 4)  # 1024-thread blocks of the pull kernels (two per reserved SM)
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    # waves of 1, 2, 4, ... ranks: the first lands under the tiles of this rank's own columns, each following one
+    # under the tiles of the wave before it
+    waves, left = [], world - 1
+    while left > 0:
+        n = min(left, 1 << len(waves)) if pipelined else left
+        waves.append(n)
+        left -= n
+    trace = _TRACE is not None
+    landed = [torch.cuda.Event(enable_timing=trace) for _ in waves]
+    after_barrier = torch.cuda.Event(enable_timing=True) if trace else None
+
+    def start_pulls():
+        with torch.cuda.stream(comm):
+            comm.wait_event(ready)
+            hdl.barrier(0)  # every rank's own shard is normalised and in place
+            if trace:
+                after_barrier.record(comm)
+            first = 1
+            for n, ev in zip(waves, landed):
+                be.pull_shards(ws, first, n, blocks)
+                ev.record(comm)
+                first += n
+        if trace:
+            global _LAST_COMM_EVENTS
+            _LAST_COMM_EVENTS = [("fwd_barrier", after_barrier)] + [(f"pull{i + 1}", ev) for i, ev in enumerate(landed)]
+
+    if pipelined:
+        lo = off // 256
+        prev = be.set_max_sms(_sm_count(dev) - cfg.comm_sms)  # the pull kernels run on the SMs left free
+        try:
+            be.forward_tiles_cols(ws, t3, 7, lo, lo + tiles_per_rank, stash)
+            start_pulls()
+            _mark("forward_tiles_local")
+            begin = (lo + tiles_per_rank) % lay.col_tiles
+            for i, (n, ev) in enumerate(zip(waves, landed)):
+                cur.wait_event(ev)
+                if i == len(waves) - 1:
+                    be.set_max_sms(prev)  # nothing left to pull: the last (largest) wave's tiles take every SM
+                be.forward_tiles_cols(ws, t3, 7, begin, begin + n * tiles_per_rank, stash, wrap=True)
+                begin = (begin + n * tiles_per_rank) % lay.col_tiles
+                if i < len(waves) - 1:
+                    _mark(f"forward_tiles_wave{i + 1}")
+        finally:
+            be.set_max_sms(prev)
+    else:
+        start_pulls()
+        cur.wait_event(landed[-1])
+        be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
+    _mark("forward_tiles")
+    be.forward_reduce(ws)
+    _mark("forward_reduce")
+    # column statistics of every rank, read from the peers; then this rank's loss share, summed the same way
+    col_all = torch.empty((world, 3, pb.rows_global), dtype=torch.float32, device=dev)
+    hdl.barrier(1)
+    _mark("forward_barrier1")
+    be.pull_col_lse(ws, col_all)
+    be.forward_loss(ws, col_all, None)
+    hdl.barrier(2)
+    be.pull_loss(ws, loss3)
+    _mark("forward_finish")
+    return loss3
+
+
 def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveConfig):
     be = _BACKEND
     pb, lay = ws.pb, ws.lay
@@ -412,7 +566,38 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
         def scatter():  # reduce-scatter of the column-role partial gradients: one coalesced NCCL launch
             _reduce_scatter([(col[m].view(-1), part[m].view(-1)) for m in range(3)], cfg.process_group, img.is_cuda)
 
-        if not (cfg.overlap and img.is_cuda):
+        if isinstance(ws, _SymmWorkspace):
+            # column role first; its partial sums are then pulled and summed straight from the peers' workspaces
+            # (NVLink loads, side stream) while the row-role GEMMs run on the remaining SMs
+            cur = torch.cuda.current_stream()
+            comm = _comm_stream(img.device)
+            be.backward_gemms_role(ws, t3, g3, 1, fused)
+            _mark("backward_gemms_col")
+            done = torch.cuda.Event()
+            done.record(cur)
+            trace = _TRACE is not None
+            reduced = torch.cuda.Event(enable_timing=trace)
+            bar_done = torch.cuda.Event(enable_timing=True) if trace else None
+            with torch.cuda.stream(comm):
+                comm.wait_event(done)
+                ws.hdl.barrier(0)  # every rank's column-role partial sums are complete
+                if trace:
+                    bar_done.record(comm)
+                be.pull_reduce_cols(ws, 4 * max(cfg.comm_sms, 4))
+                reduced.record(comm)
+            if trace:
+                global _LAST_COMM_EVENTS
+                _LAST_COMM_EVENTS = (_LAST_COMM_EVENTS or []) + [("bwd_barrier", bar_done), ("pull_reduce", reduced)]
+            prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms) if cfg.overlap else None
+            try:
+                be.backward_gemms_role(ws, t3, g3, 2, fused)
+            finally:
+                if prev is not None:
+                    be.set_max_sms(prev)
+            _mark("backward_gemms_row")
+            cur.wait_event(reduced)
+            _mark("backward_gemms")
+        elif not (cfg.overlap and img.is_cuda):
             be.backward_gemms_role(ws, t3, g3, 0, fused)
             _mark("backward_gemms")
             scatter()
@@ -451,7 +636,7 @@ class _TriContrastive(torch.autograd.Function):
     def forward(ctx, img, txt, aud, t3, cfg):
         img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
         pb, _, _ = _make_problem(img, cfg)
-        ws = _POOL.acquire(pb, img.device)
+        ws = _POOL.acquire(pb, img.device, cfg.process_group if _use_p2p(cfg, img) else None)
         lease = _Lease(ws)
         loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         ctx.save_for_backward(img, txt, aud, t3)
@@ -487,7 +672,7 @@ def fused_tri_contrastive(img: torch.Tensor, txt: torch.Tensor, aud: torch.Tenso
     else:  # eval loops run under torch.no_grad() (main_pretraining.py:192-210): nothing is kept for backward
         img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
         pb, _, _ = _make_problem(img, cfg)
-        ws = _POOL.acquire(pb, img.device)
+        ws = _POOL.acquire(pb, img.device, cfg.process_group if _use_p2p(cfg, img) else None)
         try:
             loss3 = _forward_impl(ws, img.detach(), txt.detach(), aud.detach(), t3.detach(), cfg)
         finally:
@@ -500,7 +685,7 @@ def forward_backward_raw(img, txt, aud, t3, g3, config: Optional[TriContrastiveC
     cfg = config or _DEFAULT
     _check_inputs(img, txt, aud)
     pb, _, _ = _make_problem(img, cfg)
-    ws = _POOL.acquire(pb, img.device)
+    ws = _POOL.acquire(pb, img.device, cfg.process_group if _use_p2p(cfg, img) else None)
     try:
         loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, cfg)

@@ -1,5 +1,6 @@
-"""GPU, world_size >= 2 over NCCL: the row-sharded CUDA path against the oracle on the concatenated global batch
-(SURVEY 8e).  Skipped on single-GPU boxes."""
+"""GPU, world_size >= 2: the row-sharded CUDA path against the oracle on the concatenated global batch,
+with both transports -- peer-memory pulls over symmetric memory ("p2p") and torch.distributed NCCL collectives
+("nccl").  Skipped on single-GPU boxes."""
 import os
 import socket
 
@@ -21,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, rows_local, dim, dtype_name, math_mode, grad_scale, out_dir):
+def _worker(rank, world, port, rows_local, dim, dtype_name, math_mode, grad_scale, transport, out_dir):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -41,8 +42,9 @@ def _worker(rank, world, port, rows_local, dim, dtype_name, math_mode, grad_scal
         t3 = torch.tensor(T3, dtype=torch.float32, device="cuda")
         g3 = torch.tensor(W3, dtype=torch.float32, device="cuda")
         cfg = ops.TriContrastiveConfig(process_group=dist.group.WORLD, math=math_mode, grad_scale=grad_scale,
-                                       grads_fp32=True)
-        loss3, dimg, dtxt, daud, dt3 = ops.forward_backward_raw(*ten, t3, g3, cfg)
+                                       grads_fp32=True, transport=transport)
+        for _ in range(3):  # repeated steps reuse the workspace: the cross-step ordering of the exchanges is exercised
+            loss3, dimg, dtxt, daud, dt3 = ops.forward_backward_raw(*ten, t3, g3, cfg)
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), loss=loss3.double().cpu().numpy(),
                  dscale=dt3.double().cpu().numpy(), dimg=dimg.double().cpu().numpy(),
@@ -51,18 +53,21 @@ def _worker(rank, world, port, rows_local, dim, dtype_name, math_mode, grad_scal
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("rows_local,dim,dtype_name,math_mode,grad_scale,tol", [
     (320, 256, "float32", "f16x3", "ddp", 1e-5),
     (1000, 512, "bfloat16", "f16", "ddp", 1e-3),
     (96, 64, "float32", "f16", "sum", 1e-3),
+    (512, 768, "bfloat16", "f16", "ddp", 1e-3),   # whole 256-column tiles per rank: the pipelined (wave) schedule
 ])
-def test_ranks_match_global_batch_oracle(tmp_path, rows_local, dim, dtype_name, math_mode, grad_scale, tol):
+def test_ranks_match_global_batch_oracle(tmp_path, rows_local, dim, dtype_name, math_mode, grad_scale, tol, transport):
     import torch.multiprocessing as mp
 
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
-    mp.spawn(_worker, args=(world, _free_port(), rows_local, dim, dtype_name, math_mode, grad_scale, str(tmp_path)),
+    mp.spawn(_worker, args=(world, _free_port(), rows_local, dim, dtype_name, math_mode, grad_scale, transport,
+                            str(tmp_path)),
              nprocs=world, join=True)
     embs = closed_form.synthetic_embeddings(rows_local * world, dim, 321, 0.2)
     if dtype_name == "bfloat16":

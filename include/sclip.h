@@ -194,6 +194,15 @@ int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* im
                           const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,
                           void* dtxt, void* daud, int out_f32, int flags, float* dt3, void* stream);
 
+/* ---- zero-shot scorers (model.py:126-203 get_img_txt_sim_score / get_aud_txt_sim_score, and the return_logits
+ * branch model.py:275-277): logits = exp(*log_scale) * unit(a) . unit(b)^T, MATERIALISED (m x n, n = number of
+ * prompts / classes).  Same normalise kernel and tile kernel as the training path with a store epilogue.
+ * a: (m, dim), b: (n, dim) row-major, dtype SCLIP_F32 | SCLIP_BF16; logits: (m, ldc) fp32 with ldc >= n rounded up to
+ * a multiple of 4 (columns [n, ldc) receive zeros); scratch: sclip_cosine_logits_scratch bytes, 256-byte aligned. */
+int sclip_cosine_logits_scratch(int m, int n, int dim, int math, uint64_t* bytes);
+int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, int m, int n, int dim, int dtype, int math,
+                        void* scratch, float* logits, int64_t ldc, void* stream);
+
 /* ---- peer-memory exchanges (world > 1) ------------------------------------------------------------
  * When every rank's workspace lives in symmetric memory (mapped into all processes of the node over NVLink /
  * NVSwitch), the exchanges the reference would do with torch.distributed collectives are kernels of this library that

@@ -164,6 +164,7 @@ struct GemmParams {
   const float* fac;  // base of the conversion factor vectors (Segment::transform)
   const float* t3;   // when non-null alpha = alpha0 * max_q |exp(t_q) g_q| (backward); else alpha = alpha0
   const float* g3;
+  const float* log_alpha;  // when non-null alpha is further multiplied by exp(*log_alpha) (zero-shot scorers)
   float alpha0;
 };
 
@@ -187,6 +188,9 @@ int launch_backward_finish(const Workspace& w, const void* const x3[3], const fl
                            const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, int stash,
                            float* dt3, cudaStream_t stream);
 int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream);
+// rows x dim matrix -> unit rows as fp16 operands (hi, and lo when split), times opscale
+int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __half* lo, float* inv_norm, bool split,
+                     cudaStream_t stream);
 // peer-memory exchanges (world > 1, workspaces in symmetric memory); peer_ws[r] = base of rank r's workspace
 int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
                        cudaStream_t stream);

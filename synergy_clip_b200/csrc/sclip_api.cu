@@ -73,7 +73,9 @@ int wide_width(int n) {
 }
 
 // k splits per tile so that the persistent clusters finish together: minimise rounds x (k blocks per unit + fixed
-// cost of a unit: ring fill and epilogue, about 8 k-block times), keeping at least 32 k blocks per unit
+// cost of a unit: ring fill and epilogue, about 8 k-block times), keeping at least 32 k blocks per unit.  At most two:
+// the partial sums meet in a zeroed output through fp32 red.add, and 0 + a + b does not depend on the arrival order
+// (IEEE addition is commutative) whereas three or more addends would make the result run-to-run non-deterministic.
 int wide_ksplits(int tiles, int kb) {
   int sms = 148;
   {
@@ -85,10 +87,10 @@ int wide_ksplits(int tiles, int kb) {
   if (max_sms() > 0 && max_sms() < sms) sms = max_sms();
   const int clusters = sms / 2 > 0 ? sms / 2 : 1;
   const char* e = getenv("SCLIP_KSPLITS");  // profiling experiments only
-  if (e != nullptr && atoi(e) >= 1) return atoi(e);
+  if (e != nullptr && atoi(e) >= 1) return atoi(e) > kb ? kb : atoi(e);
   int best = 1;
   double best_cost = 0;
-  for (int ks = 1; ks <= 8; ++ks) {
+  for (int ks = 1; ks <= 2; ++ks) {
     if (ks > 1 && kb / ks < 32) break;
     const double cost = static_cast<double>(ceil_div(tiles * ks, clusters)) * (ceil_div(kb, ks) + 8);
     if (ks == 1 || cost < best_cost * 0.995) {
@@ -689,6 +691,75 @@ int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* im
   }
   return launch_backward_finish(w, x3, t3, g3, col_contrib, grad_mult, dx3, out_f32, (flags & SCLIP_BWD_STASHED) ? 1 : 0,
                                 dt3, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_cosine_logits_scratch(int m, int n, int dim, int math, uint64_t* bytes) {
+  if (m < 1 || n < 1 || dim < 8 || dim % 8 != 0 || bytes == nullptr ||
+      (math != SCLIP_MATH_F16 && math != SCLIP_MATH_F16X3)) {
+    set_error("sclip_cosine_logits_scratch: bad argument (m=%d n=%d dim=%d math=%d)", m, n, dim, math);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const uint64_t parts = math == SCLIP_MATH_F16X3 ? 2 : 1;
+  *bytes = parts * (align_up(static_cast<uint64_t>(m) * dim * 2, 256) + align_up(static_cast<uint64_t>(n) * dim * 2, 256)) +
+           align_up(static_cast<uint64_t>(m + n) * 4, 256);
+  return SCLIP_OK;
+}
+
+int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, int m, int n, int dim, int dtype, int math,
+                        void* scratch, float* logits, int64_t ldc, void* stream) {
+  uint64_t need = 0;
+  int rc = sclip_cosine_logits_scratch(m, n, dim, math, &need);
+  if (rc) return rc;
+  const int n4 = (n + 3) / 4 * 4;
+  if (a == nullptr || b == nullptr || log_scale == nullptr || scratch == nullptr || logits == nullptr ||
+      (dtype != SCLIP_F32 && dtype != SCLIP_BF16) || ldc < n4 || ldc % 4 != 0 ||
+      (reinterpret_cast<uintptr_t>(scratch) & 255u) != 0 || (reinterpret_cast<uintptr_t>(logits) & 15u) != 0 ||
+      (reinterpret_cast<uintptr_t>(a) & 15u) != 0 || (reinterpret_cast<uintptr_t>(b) & 15u) != 0) {
+    set_error("sclip_cosine_logits: bad argument (null / misaligned pointer, dtype, or ldc < n rounded up to 4)");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool x3 = math == SCLIP_MATH_F16X3;
+  uint8_t* base = static_cast<uint8_t*>(scratch);
+  const uint64_t abytes = align_up(static_cast<uint64_t>(m) * dim * 2, 256);
+  const uint64_t bbytes = align_up(static_cast<uint64_t>(n) * dim * 2, 256);
+  __half* a_hi = reinterpret_cast<__half*>(base);
+  __half* b_hi = reinterpret_cast<__half*>(base + abytes);
+  __half* a_lo = x3 ? reinterpret_cast<__half*>(base + abytes + bbytes) : a_hi;
+  __half* b_lo = x3 ? reinterpret_cast<__half*>(base + 2 * abytes + bbytes) : b_hi;
+  float* inv = reinterpret_cast<float*>(base + (x3 ? 2 : 1) * (abytes + bbytes));
+  rc = launch_normalise(a, dtype, m, dim, a_hi, a_lo, inv, x3, st);
+  if (!rc) rc = launch_normalise(b, dtype, n, dim, b_hi, b_lo, inv + m, x3, st);
+  if (rc) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int cg = cta_group();
+  rc = make_map(&p.maps[0], a_hi, dim, m, dim, BK, BM);
+  if (!rc) rc = make_map(&p.maps[1], b_hi, dim, n, dim, BK, BN / cg);
+  if (!rc && x3) rc = make_map(&p.maps[2], a_lo, dim, m, dim, BK, BM);
+  if (!rc && x3) rc = make_map(&p.maps[3], b_lo, dim, n, dim, BK, BN / cg);
+  if (rc) return rc;
+  Job& job = p.jobs[0];
+  const int nkb = ceil_div(dim, BK);
+  if (x3) {  // small cross terms first (see similarity_job)
+    job.seg[job.nseg++] = seg(2, 1, 0, 0, nkb);
+    job.seg[job.nseg++] = seg(0, 3, 0, 0, nkb);
+  }
+  job.seg[job.nseg++] = seg(0, 1, 0, 0, nkb);
+  job.ksplits = 1;
+  job.m_tiles = ceil_div(m, BM * cg);
+  job.n_tiles = ceil_div(n4, BN);
+  job.tile_base = 0;
+  p.out[0] = logits;
+  p.ldc[0] = ldc;
+  p.m[0] = m;
+  p.n[0] = n4;
+  p.njobs = 1;
+  p.total_tiles = job.m_tiles * job.n_tiles;
+  p.alpha0 = x3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
+  p.log_alpha = log_scale;
+  p.stages = ring_stages(0);
+  return launch_gemm(p, cg, epi_warps(), st);
 }
 
 static int check_peers(const Workspace& w, void* ws, const void* const* peer_ws) {

@@ -629,6 +629,28 @@ int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t st
   return SCLIP_OK;
 }
 
+int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __half* lo, float* inv_norm, bool split,
+                     cudaStream_t stream) {
+  PrologueArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x[0] = x;
+  a.hi[0] = hi;
+  a.lo[0] = lo;
+  a.inv_norm = inv_norm;
+  a.rows = rows;
+  a.dim = dim;
+  a.row_offset = 0;
+  a.split = split ? 1 : 0;
+  a.opscale = split ? kOperandScaleX3 : 1.0f;
+  dim3 grid((rows + kRowsPerBlock - 1) / kRowsPerBlock, 1);
+  if (dtype == SCLIP_F32)
+    prologue_kernel<float><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
+  else
+    prologue_kernel<__nv_bfloat16><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
+  SCLIP_CUDA_OK(cudaGetLastError());
+  return SCLIP_OK;
+}
+
 int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream) {
   ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.lse_row, w.lse_col_local, w.row_inv, w.col_sum_local, w.status,
                w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, row_tiles_done, w.lay.col_tiles};

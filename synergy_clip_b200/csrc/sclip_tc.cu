@@ -1347,6 +1347,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
       for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
       alpha *= mx;
     }
+    if (P.log_alpha != nullptr) alpha *= expf(*P.log_alpha);  // a learnable log-temperature read on the device
     int it = 0;
     RingState conv_ring;
     uint32_t conv_count = 0;

@@ -6,8 +6,9 @@ return modes (``/root/reference/model.py:60-281``) so that ``main_pretraining.py
 it in place of the reference class.  The only behavioural difference is *where* the pre-training branch
 (``config.is_PT``) is computed: lines 247-272 of the reference (normalise, three scaled similarity matmuls,
 three ``clip_loss``) are one call into the sm_100a library (``synergy_clip_b200.ops``), which has no CPU
-fallback.  The other return modes materialise logits / embeddings exactly like the reference and stay in
-plain PyTorch (SURVEY 8f-2 lists them as the next row to move onto the tile kernels).
+fallback.  The zero-shot scorers and the ``return_logits`` branch materialise their logits like the reference;
+under ``torch.no_grad()`` on the GPU (how ZS_task.py and friends call them) the normalise + scaled matmul run on
+the same library (``ops.cosine_logits``), otherwise the reference's own statements are executed.
 
 Knobs the reference does not have are read from the environment so that the scripts run unchanged:
   SCLIP_GLOBAL_BATCH=1   use the *global* batch as negatives: row-shard over the default process group
@@ -22,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .ops import TriContrastiveConfig, fused_tri_contrastive
+from .ops import TriContrastiveConfig, cosine_logits, fused_tri_contrastive
 
 __all__ = ["Tri_CLIP", "clip_loss", "contrastive_loss"]
 
@@ -41,6 +42,16 @@ def clip_loss(similarity: torch.Tensor) -> torch.Tensor:
 
 def _unit(x: torch.Tensor) -> torch.Tensor:
     return x / x.norm(p=2, dim=-1, keepdim=True)  # no epsilon, like model.py:248-250
+
+
+def _scaled_cosine(a: torch.Tensor, b: torch.Tensor, log_scale: torch.Tensor) -> torch.Tensor:
+    """``matmul(unit(a), unit(b).t()) * log_scale.exp()`` (model.py:160-167, 195-202, 252-265).  The evaluation callers
+    (ZS_task.py:338,344 and the ``return_logits`` consumers ZS_image_task.py:1479, ZS_audio_task.py:195) run under
+    ``torch.no_grad()`` on the GPU: those go through the library's normalise + tile kernels.  With autograd enabled, or
+    on the CPU, the reference's own three statements are executed unchanged."""
+    if a.is_cuda and not torch.is_grad_enabled() and a.dtype in (torch.float32, torch.bfloat16) and a.shape[1] % 8 == 0:
+        return cosine_logits(a, b, log_scale)
+    return torch.matmul(_unit(a), _unit(b).t()) * log_scale.exp()
 
 
 def _op_config() -> TriContrastiveConfig:
@@ -108,14 +119,14 @@ class Tri_CLIP(nn.Module):
 
     # ---- zero-shot scorers (model.py:126-203): materialised logits ------------------------------------------
     def get_img_txt_sim_score(self, pixel_values=None, input_ids=None, att_mask=None, pos_ids=None):
-        img = _unit(self.get_image_features(pixel_values))
-        txt = _unit(self.get_text_features(input_ids, att_mask, pos_ids))
-        return torch.matmul(img, txt.t()) * self.logit_scale_for_IT.exp()
+        img = self.get_image_features(pixel_values)
+        txt = self.get_text_features(input_ids, att_mask, pos_ids)
+        return _scaled_cosine(img, txt, self.logit_scale_for_IT)
 
     def get_aud_txt_sim_score(self, input_ids=None, att_mask=None, pos_ids=None, input_values=None, head_mask=None):
-        txt = _unit(self.get_text_features(input_ids, att_mask, pos_ids))
-        aud = _unit(self.get_audio_features(input_values, head_mask))
-        return torch.matmul(txt, aud.t()) * self.logit_scale_for_TA.exp()
+        txt = self.get_text_features(input_ids, att_mask, pos_ids)
+        aud = self.get_audio_features(input_values, head_mask)
+        return _scaled_cosine(txt, aud, self.logit_scale_for_TA)
 
     # ---- forward (model.py:205-281) -------------------------------------------------------------------------
     def forward(self, pixel_values=None, input_ids=None, att_mask=None, pos_ids=None, input_values=None,
@@ -132,12 +143,12 @@ class Tri_CLIP(nn.Module):
             return fused_tri_contrastive(img, txt, aud, self.logit_scale_for_IT, self.logit_scale_for_TA,
                                          self.logit_scale_for_AI, config=_op_config())
 
-        img, txt, aud = _unit(img), _unit(txt), _unit(aud)
         if self.config.return_logits:
-            logits = (torch.matmul(img, txt.t()) * self.logit_scale_for_IT.exp(),
-                      torch.matmul(txt, aud.t()) * self.logit_scale_for_TA.exp(),
-                      torch.matmul(aud, img.t()) * self.logit_scale_for_AI.exp())
-            return logits, img, txt, aud
+            logits = (_scaled_cosine(img, txt, self.logit_scale_for_IT),
+                      _scaled_cosine(txt, aud, self.logit_scale_for_TA),
+                      _scaled_cosine(aud, img, self.logit_scale_for_AI))
+            return logits, _unit(img), _unit(txt), _unit(aud)
+        img, txt, aud = _unit(img), _unit(txt), _unit(aud)
         if self.config.return_lhs:
             return vision_out[0], text_out[0], audio_out[0]
         return img, txt, aud

@@ -23,7 +23,7 @@ import torch
 from . import _lib
 from ._lib import MATH_F16, MATH_F16X3, Problem, SCLIP_BF16, SCLIP_F32
 
-__all__ = ["fused_tri_contrastive", "TriContrastiveConfig", "gemm_f16", "workspace_bytes"]
+__all__ = ["fused_tri_contrastive", "TriContrastiveConfig", "cosine_logits", "gemm_f16", "workspace_bytes"]
 
 
 class TriContrastiveConfig:
@@ -711,3 +711,44 @@ def gemm_f16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = 
     _lib.check(lib.sclip_gemm_f16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(c), n, m, n, k,
                                   ctypes.c_float(alpha), _stream()), "sclip_gemm_f16")
     return c
+
+
+_SCRATCH = {}
+
+
+def cosine_logits(a: torch.Tensor, b: torch.Tensor, log_scale: torch.Tensor, math: str = "auto") -> torch.Tensor:
+    """``exp(log_scale) * unit(a) @ unit(b).T`` as a materialised (M, N) fp32 matrix -- the arithmetic of the reference's
+    zero-shot scorers (``get_img_txt_sim_score`` / ``get_aud_txt_sim_score``, model.py:126-203) and of its
+    ``return_logits`` branch (model.py:275-277) on the library's normalise + tile kernels.  Forward only (the reference
+    calls these under ``torch.no_grad()``: ZS_task.py:338,344); CUDA only, no CPU fallback."""
+    lib = _lib.load()
+    if not a.is_cuda or not b.is_cuda:
+        raise _lib.SclipError("cosine_logits only runs on a CUDA (sm_100a) device and has no CPU fallback")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or a.dtype != b.dtype:
+        raise ValueError("cosine_logits takes (M, D) and (N, D) matrices of one dtype")
+    if a.dtype == torch.float32:
+        dtype = SCLIP_F32
+    elif a.dtype == torch.bfloat16:
+        dtype = SCLIP_BF16
+    else:
+        raise TypeError(f"embeddings must be float32 or bfloat16, got {a.dtype}")
+    if math == "auto":
+        math = "f16x3" if dtype == SCLIP_F32 else "f16"
+    mode = MATH_F16X3 if math == "f16x3" else MATH_F16
+    a, b = a.detach().contiguous(), b.detach().contiguous()
+    m, d = a.shape
+    n = b.shape[0]
+    need = ctypes.c_uint64()
+    _lib.check(lib.sclip_cosine_logits_scratch(m, n, d, mode, byref(need)), "sclip_cosine_logits_scratch")
+    key = (a.device.index, int(need.value))
+    scratch = _SCRATCH.get(key)
+    if scratch is None:
+        raw = torch.empty(int(need.value) + 256, dtype=torch.uint8, device=a.device)
+        skew = (-raw.data_ptr()) % 256
+        scratch = _SCRATCH[key] = raw[skew:skew + int(need.value)]
+    ldc = (n + 3) // 4 * 4
+    out = torch.empty((m, ldc), dtype=torch.float32, device=a.device)
+    t = log_scale.detach().reshape(1).to(device=a.device, dtype=torch.float32)
+    _lib.check(lib.sclip_cosine_logits(_ptr(a), _ptr(b), _ptr(t), m, n, d, dtype, mode, _ptr(scratch), _ptr(out), ldc,
+                                       _stream()), "sclip_cosine_logits")
+    return out[:, :n]

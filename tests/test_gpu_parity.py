@@ -153,3 +153,29 @@ def test_large_scale_properties_full_size():
     want = closed_form.tri_contrastive(*[s.float().cpu().numpy() for s in sub], (2.6592,) * 3, want_grads=False)
     got = ops.forward_backward_raw(*[s.contiguous() for s in sub], t3, g3, cfg)[0]
     assert np.max(np.abs(got.cpu().numpy() - want["loss"]) / want["loss"]) < TOL_F16
+
+
+# ---- zero-shot scorers (model.py:126-203, 275-277) on the normalise + tile kernels ---------------------
+@pytest.mark.parametrize("m,n,d,dtype_name,math_mode,tol", [
+    (128, 1000, 512, "float32", "f16x3", 1e-5),
+    (37, 10, 768, "float32", "f16x3", 1e-5),
+    (300, 397, 512, "bfloat16", "f16", 1e-3),
+    (1, 527, 768, "float32", "f16", 1e-3),     # one sample against every prompt, the reference's ZS loop (ZS_task.py:338)
+])
+def test_cosine_logits_match_reference_expression(m, n, d, dtype_name, math_mode, tol):
+    import torch
+
+    from synergy_clip_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    dtype = getattr(torch, dtype_name)
+    a = torch.randn(m, d, generator=g).to(dtype)
+    b = torch.randn(n, d, generator=g).to(dtype)
+    t = torch.tensor(2.6592)
+    # the reference's three statements (model.py:160-167) in fp64 on the same (rounded) inputs
+    a64, b64 = a.double(), b.double()
+    want = (a64 / a64.norm(p=2, dim=-1, keepdim=True)) @ (b64 / b64.norm(p=2, dim=-1, keepdim=True)).t() * t.double().exp()
+    got = ops.cosine_logits(a.cuda(), b.cuda(), t.cuda(), math=math_mode).double().cpu()
+    assert got.shape == (m, n)
+    err = ((got - want) ** 2).sum().sqrt() / (want ** 2).sum().sqrt()
+    assert err < tol, err

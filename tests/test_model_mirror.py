@@ -165,3 +165,27 @@ def test_dropin_shim_reexports_reference_names():
                PYTHONPATH=os.pathsep.join([os.path.join(root, "dropin"), root]))
     res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_zero_shot_scorers_on_gpu_match_the_reference_expression(tiny_encoders):
+    """ZS_task.py:338,344 call the scorers under no_grad on the GPU: that path runs on the library and
+    must agree with the reference's own three statements (model.py:160-167), which the same method executes when
+    autograd is enabled."""
+    from synergy_clip_b200.model import Tri_CLIP
+
+    m = Tri_CLIP(_tiny_config(is_pt=False, return_logits=True)).cuda().eval()
+    batch = _batch(9, "cuda")
+    it_args = {k: v for k, v in batch.items() if k != "input_values"}
+    ta_args = {k: v for k, v in batch.items() if k != "pixel_values"}
+    with torch.no_grad():
+        fused_it = m.get_img_txt_sim_score(**it_args)
+        fused_ta = m.get_aud_txt_sim_score(**ta_args)
+        fused_logits, _, _, _ = m(**batch)
+    plain_it = m.get_img_txt_sim_score(**it_args).detach()
+    plain_ta = m.get_aud_txt_sim_score(**ta_args).detach()
+    plain_logits, _, _, _ = m(**batch)
+    for got, want in ((fused_it, plain_it), (fused_ta, plain_ta), *zip(fused_logits, plain_logits)):
+        want = want.detach()
+        assert got.shape == want.shape
+        assert ((got - want).norm() / want.norm()).item() < 1e-5

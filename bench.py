@@ -35,7 +35,7 @@ def load_traffic(b, d, world):
         with open(path) as f:
             t = json.load(f)
         if t.get("rows_global") == b and t.get("dim") == d and t.get("world") == world:
-            return t.get("gemm_tiles_kernel_dram_bytes")
+            return t.get("gemm_wide_kernel_dram_bytes")
     except Exception:  # noqa: BLE001
         pass
     return None
@@ -294,9 +294,18 @@ def main():
         def resident_step():
             out["r"] = ops.forward_backward_raw(*embs, t3, g3, cfg)
 
+        from synergy_clip_b200 import _lib as sclip_lib
+
+        counter = sclip_lib.load().sclip_kernel_launches
+        # warm up outside the counted / clock-sampled window, then time exactly `steps` steps
+        for _ in range(warmup):
+            resident_step()
+        torch.cuda.synchronize()
+        launches0 = counter()
         sampler = ClockSampler(local_rank)
         with sampler:
-            ms = time_steps(resident_step, steps, warmup, dist if shard else None)
+            ms = time_steps(resident_step, steps, 0, dist if shard else None)
+        launches = counter() - launches0
         stages = stage_breakdown(resident_step, min(steps, 5))
 
         # end to end through the public autograd API with HOST buffers: every step copies its three embedding matrices
@@ -333,7 +342,12 @@ def main():
 
         ms_e2e = time_steps(e2e_step, steps, warmup, dist if shard else None)
         h2d = sum(h.numel() * h.element_size() for h in host)
+        if shard and dist is not None:
+            lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+            dist.all_reduce(lt)
+            launches = int(lt.item())
         return {"ms": ms, "ms_e2e": ms_e2e, "stages": stages, "clocks": sampler.summary(), "h2d": h2d,
+                "launches": launches,
                 "loss": [float(x) for x in out["r"][0].tolist()], "rows_local": embs[0].shape[0]}
 
     b, d = WORKLOADS[args.workload]
@@ -385,8 +399,8 @@ def main():
             "clocks": main_res["clocks"],
             "e2e": {"value": b / (main_res["ms_e2e"] * 1e-3), "unit": "samples/s", "ms_per_step": main_res["ms_e2e"],
                     "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": 12},
-            "gpu_launches": 8 * args.steps,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tiles_kernel (backward_gemms)", "achieved": gemm_tf,
+            "gpu_launches": main_res["launches"],  # kernels of libsclip.so launched in the timed region, all ranks
+            "roofline": {"bound": "tensor", "kernel": "gemm_wide_kernel (backward_gemms)", "achieved": gemm_tf,
                          "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": (gemm_tf / peaks["bf16_tflops"]) if gemm_tf else None,
                          "traffic": load_traffic(b, d, world),

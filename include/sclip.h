@@ -103,6 +103,8 @@ typedef struct sclip_layout {
 
 int sclip_abi_version(void);
 const char* sclip_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process so far (all threads). */
+long long sclip_kernel_launches(void);
 
 /* Workspace sizing.  Pure host arithmetic; callable without a GPU. */
 int sclip_plan(const sclip_problem* problem, sclip_layout* layout);

@@ -42,6 +42,7 @@ class SclipError(RuntimeError):
 _PROTOTYPES = {
     "sclip_abi_version": (c_int, []),
     "sclip_last_error": (c_char_p, []),
+    "sclip_kernel_launches": (ctypes.c_longlong, []),
     "sclip_plan": (c_int, [POINTER(Problem), POINTER(Layout)]),
     "sclip_prologue": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_forward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p]),

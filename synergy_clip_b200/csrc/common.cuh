@@ -72,6 +72,14 @@ void set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+// every kernel launch of the library is counted (sclip_kernel_launches: the bench reports it as gpu_launches)
+void count_launch();
+#define SCLIP_LAUNCHED()                     \
+  do {                                       \
+    ::sclip::count_launch();                 \
+    SCLIP_CUDA_OK(cudaGetLastError());       \
+  } while (0)
+
 // pair p: rows = modality p, cols = modality (p + 1) % 3  (model.py:255,260,265)
 __host__ __device__ inline int pair_row_modality(int p) { return p; }
 __host__ __device__ inline int pair_col_modality(int p) { return (p + 1) % 3; }

@@ -1,5 +1,6 @@
 // C ABI of the sclip library (include/sclip.h): argument checking, workspace layout, TMA descriptor
 // construction and the stage launchers.  Host code only; the kernels live in sclip_tc.cu / sclip_simt.cu.
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,9 @@ int cta_group() {
   }
   return cached;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static int g_max_sms = 0;
 int max_sms() { return g_max_sms; }
@@ -360,6 +364,7 @@ using namespace sclip;
 extern "C" {
 
 int sclip_abi_version(void) { return SCLIP_ABI_VERSION; }
+long long sclip_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* sclip_last_error(void) { return g_error; }
 
 int sclip_plan(const sclip_problem* problem, sclip_layout* layout) { return plan(problem, layout); }

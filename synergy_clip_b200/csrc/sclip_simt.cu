@@ -146,12 +146,22 @@ __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a)
     const int ti = i / BM;
     const float* ref = a.tile_ref + (static_cast<size_t>(p) * a.nti + ti) * a.ntj;
     float R = -INFINITY;
-    for (int tj = 0; tj < a.ntj; ++tj) R = fmaxf(R, ref[tj]);
-    float sum = 0.f;
-    for (int tj = 0; tj < a.ntj; ++tj) {  // two slots per column tile (one per 128-column slice)
-      const float* rp = a.row_part + (static_cast<size_t>(p) * a.ntj * 2 + tj * 2) * a.rows_local + i;
-      sum += (rp[0] + rp[a.rows_local]) * __expf(ref[tj] - R);
+    for (int tj = 0; tj < a.ntj; ++tj) R = fmaxf(R, __ldg(ref + tj));
+    // four independent partial sums keep the (coalesced) loads of several column tiles in flight
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float* rp0 = a.row_part + static_cast<size_t>(p) * a.ntj * 2 * a.rows_local + i;
+    const size_t pitch = static_cast<size_t>(2) * a.rows_local;  // two slots per column tile (one per 128-column slice)
+    auto term = [&](int tj) {
+      const float* rp = rp0 + tj * pitch;
+      return (__ldg(rp) + __ldg(rp + a.rows_local)) * __expf(__ldg(ref + tj) - R);
+    };
+    int tj = 0;
+    for (; tj + 3 < a.ntj; tj += 4) {
+      const float t0 = term(tj), t1 = term(tj + 1), t2 = term(tj + 2), t3 = term(tj + 3);
+      s0 += t0; s1 += t1; s2 += t2; s3 += t3;
     }
+    for (; tj < a.ntj; ++tj) s0 += term(tj);
+    const float sum = (s0 + s1) + (s2 + s3);
     const float lse = R + logf(sum);
     a.lse_row[static_cast<size_t>(p) * a.rows_local + i] = lse;
     a.row_inv[static_cast<size_t>(p) * a.rows_local + i] = 1.0f / sum;  // meaningful when every tile reference is 0
@@ -161,10 +171,18 @@ __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a)
     const int tj = i / BN;
     float R = -INFINITY;
     for (int ti = 0; ti < a.nti_done; ++ti) R = fmaxf(R, a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj]);
-    float sum = 0.f;
-    for (int ti = 0; ti < a.nti_done; ++ti)
-      sum += a.col_part[(static_cast<size_t>(p) * a.nti + ti) * a.rows_global + i] *
-             __expf(a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj] - R);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    auto term = [&](int ti) {
+      return __ldg(a.col_part + (static_cast<size_t>(p) * a.nti + ti) * a.rows_global + i) *
+             __expf(__ldg(a.tile_ref + (static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj) - R);
+    };
+    int ti = 0;
+    for (; ti + 3 < a.nti_done; ti += 4) {
+      const float t0 = term(ti), t1 = term(ti + 1), t2 = term(ti + 2), t3 = term(ti + 3);
+      s0 += t0; s1 += t1; s2 += t2; s3 += t3;
+    }
+    for (; ti < a.nti_done; ++ti) s0 += term(ti);
+    const float sum = (s0 + s1) + (s2 + s3);
     const float lse = R + logf(sum);
     a.lse_col_local[static_cast<size_t>(p) * a.rows_global + i] = lse;
     a.col_sum_local[static_cast<size_t>(p) * a.rows_global + i] = sum;
@@ -625,7 +643,7 @@ int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t st
     prologue_kernel<float><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
   else
     prologue_kernel<__nv_bfloat16><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -647,7 +665,7 @@ int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __
     prologue_kernel<float><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
   else
     prologue_kernel<__nv_bfloat16><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -657,7 +675,7 @@ int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t s
   const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
   dim3 grid((n + 255) / 256, 3);
   forward_reduce_kernel<<<grid, 256, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -665,7 +683,7 @@ int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* los
   LossArgs a{w.lse_row, w.lse_col_local, col_lse_all, w.diag, w.col_sum_local, w.lse_col, w.col_inv, w.loss_part, loss3,
              w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, w.pb.world};
   forward_loss_kernel<<<3, 1024, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -698,12 +716,12 @@ int launch_backward_finish(const Workspace& w, const void* const x3[3], const fl
     backward_finish_kernel<__nv_bfloat16, float><<<grid, threads, 0, stream>>>(a);
   else
     backward_finish_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, threads, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   if (dt3 != nullptr) {
     DtArgs dd{w.dt_part, w.dot_part, t3, g3, dt3, w.lay.row_tiles * w.lay.col_tiles, static_cast<int>(grid.x),
               w.pb.rows_global, stash, grad_mult};
     dt_finish_kernel<<<1, 1024, 0, stream>>>(dd);
-    SCLIP_CUDA_OK(cudaGetLastError());
+    SCLIP_LAUNCHED();
   }
   return SCLIP_OK;
 }
@@ -718,7 +736,7 @@ int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream) {
   a.rows_global = w.pb.rows_global;
   a.row_offset = w.pb.row_offset;
   diag_kernel<<<(a.rows + kRowsPerBlock - 1) / kRowsPerBlock, kRowsPerBlock * 32, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -728,12 +746,12 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
                w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, ld_row, ld_col};
   const int n = ld_row > ld_col ? ld_row : ld_col;
   backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   if (factors_only) return SCLIP_OK;
   ScaleArgs a{w.g[0], w.fac_row, w.fac_col, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col};
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);
   backward_scale_kernel<<<grid, 256, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -762,7 +780,7 @@ int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first
   int bx = max_blocks / count;
   if (bx < 1) bx = 1;
   pull_shards_kernel<<<dim3(bx, count), 1024, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -784,7 +802,7 @@ int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_b
     case 8: pull_reduce_kernel<8><<<blocks, 512, 0, stream>>>(a); break;
     default: pull_reduce_kernel<0><<<blocks, 512, 0, stream>>>(a); break;
   }
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
@@ -799,7 +817,7 @@ int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t s
   a.count = count;
   if (sum_loss) pull_loss_kernel<<<1, 32, 0, stream>>>(a);
   else pull_stats_kernel<<<dim3((count + 1023) / 1024 > 32 ? 32 : (count + 1023) / 1024, w.pb.world), 256, 0, stream>>>(a);
-  SCLIP_CUDA_OK(cudaGetLastError());
+  SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 

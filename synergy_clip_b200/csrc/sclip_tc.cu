@@ -1718,6 +1718,7 @@ int launch_persistent(void (*kernel)(Params), const Params& p, int cg, int ew, i
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  count_launch();
   SCLIP_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p));
   return SCLIP_OK;
 }
@@ -1786,7 +1787,10 @@ int launch_gemm_wide(const GemmParams& p, int ew, cudaStream_t stream) {
   const int smem = p.stages * (A_STAGE_BYTES + p.wn * 64) + 1024;
   // SCLIP_MCAST=1 (experiment, off by default): two pairs per cluster share the A tiles by TMA multicast when every
   // job has exactly two n tiles.  Measured on B200 (32768 x 768 x 32768): 850 TFLOP/s against 1355 TFLOP/s for
-  // independent pairs -- the lockstep of four CTAs costs more than the 20 % of L2 reads it saves.
+  // independent pairs.  The same four-CTA clusters with every pair loading its own A copy (lockstep only) reach 830:
+  // it is the coupling of two pairs through one set of barriers that costs, not the multicast.  Pacing independent
+  // partner clusters through progress counters in global memory (so that the second reader of an A line hits L2) was
+  // also tried: the polling stalls the producer and the DRAM traffic did not drop (18.5 GB against 19.1 GB).
   static const bool mcast_on = [] {
     const char* e = getenv("SCLIP_MCAST");
     return e != nullptr && e[0] == '1';

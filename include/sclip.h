@@ -157,13 +157,15 @@ int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_
 int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
 /* The same tiles without recomputation, after a forward with SCLIP_FWD_STASH: in place on grad_tiles,
- *   G'_ij = E~_ij (R1_i C1_j + R2_i C2_j)  (= kappa c_p (softmax_rows + softmax_cols)/2; the "- kappa c_p I" term is
- * applied by sclip_backward_finish with SCLIP_BWD_STASHED).  HBM-bound elementwise pass. */
+ *   G'_ij = E~_ij (R1_i C1_j + R2_i C2_j) - kappa c_p [i == j]   (= kappa c_p ((softmax_rows + softmax_cols)/2 - I));
+ * the identity term is subtracted in fp32 before the rounding to fp16, so the positive-pair entry keeps its
+ * precision when the softmax is sharply peaked.  HBM-bound elementwise pass. */
 int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
-/* Only the factor vectors R1, R2, C1, C2 of that conversion; the gradient GEMMs then convert the stashed tiles in
- * shared memory on their way to the tensor cores (sclip_backward_gemms_role with SCLIP_BWD_STASHED) and the HBM pass
- * of sclip_backward_scale disappears. */
+/* Only the factor vectors R1, R2, C1, C2 of that conversion (round-1 experiment: with sclip_backward_gemms_role and
+ * SCLIP_BWD_STASHED the gradient GEMMs convert the stashed tiles in shared memory on their way to the tensor cores --
+ * measured slower than the HBM pass, and WITHOUT the identity term, which that experiment applied separately; not used
+ * by the Python op). */
 int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
 /* dxhat_row[m] = G'_{rowpair(m)} . xhat_{col modality}   (rows_local x dim, complete)
@@ -190,7 +192,8 @@ int sclip_set_max_sms(int max_sms);
  * (1, or world when the caller's DDP wrapper will average over ranks).  Also finishes dlogit_scale:
  * dt3[p] = grad_mult * (this rank's share), device, 3 floats.
  * dimg/dtxt/daud have the dtype of the problem unless out_f32 != 0.
- * flags & SCLIP_BWD_STASHED: the tiles came from sclip_backward_scale (see there). */
+ * flags & SCLIP_BWD_STASHED: the tiles came from sclip_backward_scale: dlogit_scale is then derived from the row dots
+ * <xhat, dxhat> this kernel computes anyway (no tile kernel has summed G' cos). */
 #define SCLIP_BWD_STASHED 1
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                           const float* t3, const float* g3, const float* col_contrib, float grad_mult, void* dimg,

@@ -869,9 +869,9 @@ int sclip_backward(const sclip_problem* problem, void* ws, const void* img, cons
     return SCLIP_ERR_ARGUMENT;
   }
   const bool stashed = ws != nullptr && g_stashed_ws == ws;
-  int rc = stashed ? sclip_backward_factors(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
-  if (!rc)
-    rc = sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, stashed ? SCLIP_BWD_STASHED : 0, stream);
+  int rc = stashed ? sclip_backward_scale(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
+  if (stashed) g_stashed_ws = nullptr;  // converted in place: this stash serves one backward
+  if (!rc) rc = sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, stream);
   if (!rc)
     rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32,
                                stashed ? SCLIP_BWD_STASHED : 0, dt3, stream);

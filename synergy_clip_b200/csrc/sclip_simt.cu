@@ -264,9 +264,8 @@ struct FinishArgs {
 };
 
 // d x = (d - xhat <xhat, d>) / ||x||, with xhat recomputed in fp32 from the caller's embeddings.
-// Stash mode: the tiles handed to the gradient GEMMs were kappa c_p (softmax_rows + softmax_cols)/2 without the
-// "- kappa c_p I" term, whose contribution -(s_p g_p / B) xhat_partner is subtracted here, and
-// <xhat_m, dxhat_total_m> = dt_{rowpair(m)} + dt_{colpair(m)} is accumulated for dlogit_scale.
+// Stash mode: no tile kernel has summed G' cos for dlogit_scale, so <xhat_m, dxhat_total_m> = dt_{rowpair(m)} +
+// dt_{colpair(m)} is accumulated here (three equations for the three dt, solved by dt_finish_kernel).
 template <typename T, typename TO>
 __global__ void __launch_bounds__(kRowsPerBlock * 32) backward_finish_kernel(const FinishArgs a) {
   __shared__ float blockdot[kRowsPerBlock];
@@ -279,16 +278,6 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) backward_finish_kernel(con
     const T* xr = static_cast<const T*>(a.x[m]) + static_cast<size_t>(row) * a.dim;
     TO* outr = static_cast<TO*>(a.dx[m]) + static_cast<size_t>(row) * a.dim;
     const float inv = a.inv_norm[static_cast<size_t>(m) * a.rows + row];
-    // modality m is row-side in pair m (partner = column modality (m+1)%3) and column-side in pair (m+2)%3
-    // (partner = its row modality (m+2)%3)
-    const int m1 = (m + 1) % 3, m2 = (m + 2) % 3;
-    float k1 = 0.f, k2 = 0.f;
-    if (a.stash) {
-      k1 = expf(a.t3[m]) * a.g3[m] / static_cast<float>(a.rows_global);
-      k2 = expf(a.t3[m2]) * a.g3[m2] / static_cast<float>(a.rows_global);
-    }
-    const __half* p1 = a.xhat[m1] + static_cast<size_t>(row) * a.dim;
-    const __half* p2 = a.xhat[m2] + static_cast<size_t>(row) * a.dim;
     auto total = [&](int i, float (&d)[8]) {
       load8(a.dxhat_row + base + i, d);
       if (a.col_contrib != nullptr) {
@@ -296,13 +285,6 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) backward_finish_kernel(con
         load8(a.col_contrib + base + i, e);
 #pragma unroll
         for (int k = 0; k < 8; ++k) d[k] += e[k];
-      }
-      if (a.stash) {
-        float y1[8], y2[8];
-        load8(p1 + i, y1);
-        load8(p2 + i, y2);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] -= k1 * y1[k] + k2 * y2[k];
       }
     };
     for (int i = lane * 8; i < a.dim; i += 256) {
@@ -461,7 +443,7 @@ __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs 
   }
 }
 
-// In place on the fp16 strip: stash E~_ij = exp(L_ij - (L_ii + L_jj)/2) / 16  ->  G'_ij (without the -kappa c_p I term)
+// In place on the fp16 strip: stash E~_ij = exp(L_ij - (L_ii + L_jj)/2) / 16  ->  G'_ij (the -kappa c_p I term included)
 //   G'_ij = E~_ij (R1_i C1_j + R2_i C2_j),  R1 = 8 kappa c_p exp(L_ii/2 - lse_row_i), C1 = exp(L_jj/2),
 //                                            R2 = exp(L_ii/2),                       C2 = 8 kappa c_p exp(L_jj/2 - lse_col_j)
 // HBM-bound: 2 bytes in + 2 bytes out per element; each thread keeps the factors of its 8 columns in registers and
@@ -471,8 +453,11 @@ struct ScaleArgs {
   __half* g;             // [3][rows_local][ld]
   const float* fac_row;  // [3][2][ld_row]
   const float* fac_col;  // [3][2][ld_col]
+  const float* t3;
+  const float* g3;
   int rows_local, rows_global, ld;
   int ld_row, ld_col;
+  int row_offset;
 };
 
 __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) {
@@ -489,6 +474,14 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
   }
   const float* fr = a.fac_row + static_cast<size_t>(p) * 2 * a.ld_row;
   const int row0 = blockIdx.y * kScaleRows;
+  // the "- kappa c_p I" term of G' is applied to the positive-pair entry here, in fp32 before the rounding to fp16:
+  // when the softmax is sharply peaked (trained model, large scale) that entry is kappa c_p ((P_row + P_col) / 2 - 1),
+  // a small difference of two numbers close to kappa c_p, and subtracting after the rounding (as a separate fp32
+  // term behind the fp16 GEMM) loses it: measured 1.7e-3 instead of 3e-4 on the gradients at s = 43.5, cos = 0.25.
+  float mxsg = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) mxsg = fmaxf(mxsg, fabsf(expf(a.t3[r]) * a.g3[r]));
+  const float kcp = mxsg > 0.f ? kKappa * expf(a.t3[p]) * a.g3[p] / mxsg : 0.f;
 #pragma unroll 4
   for (int r = 0; r < kScaleRows; ++r) {
     const int row = row0 + r;
@@ -497,8 +490,12 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
     __half* ptr = a.g + (static_cast<size_t>(p) * a.rows_local + row) * a.ld + col;
     float v[8];
     load8(ptr, v);
+    const int dcol = a.row_offset + row - col;  // position of the positive pair inside this thread's 8 columns
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] *= fmaf(r1, c1[k], r2 * c2[k]);
+    for (int k = 0; k < 8; ++k) {
+      v[k] *= fmaf(r1, c1[k], r2 * c2[k]);
+      if (k == dcol) v[k] -= kcp;
+    }
     *reinterpret_cast<uint4*>(ptr) = pack8_half(v);
   }
 }
@@ -748,7 +745,8 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
   backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
   SCLIP_LAUNCHED();
   if (factors_only) return SCLIP_OK;
-  ScaleArgs a{w.g[0], w.fac_row, w.fac_col, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col};
+  ScaleArgs a{w.g[0], w.fac_row, w.fac_col, t3, g3, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col,
+              w.pb.row_offset};
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);
   backward_scale_kernel<<<grid, 256, 0, stream>>>(a);
   SCLIP_LAUNCHED();

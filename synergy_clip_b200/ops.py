@@ -67,7 +67,10 @@ class TriContrastiveConfig:
         # costs 2.4 ms, the in-GEMM conversion makes the GEMMs 3.4 ms slower -- the tile mainloop is already bound by
         # shared-memory bandwidth (TMA writes + tensor-core reads ~ 125 B/clk/SM), which the conversion's extra
         # read + write of every A tile exceeds.
-        self.fuse_scale = fuse_scale
+        if fuse_scale:
+            raise ValueError("fuse_scale was a round-1 experiment (stash converted inside the gradient GEMMs): slower than "
+                             "the HBM pass and without the fp32 identity term of sclip_backward_scale; removed")
+        self.fuse_scale = False
         # world_size > 1: how the shards move between ranks.
         #   "p2p"  -- the workspace lives in symmetric memory (torch.distributed._symmetric_memory: every rank's blob
         #             mapped into every process over NVLink / NVSwitch) and the exchanges are kernels of the library

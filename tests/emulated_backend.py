@@ -173,7 +173,9 @@ class EmulatedBackend:
             hr, hc = 0.5 * dg[p, off:off + bl], 0.5 * dg[p]
             fac = (k8 * torch.exp(hr - lse_row[p]))[:, None] * torch.exp(hc)[None, :] + \
                 torch.exp(hr)[:, None] * (k8 * torch.exp(hc - lse_col[p]))[None, :]
-            g[p, :, :bg] = (g[p, :, :bg].double() * fac).half()
+            gp = g[p, :, :bg].double() * fac
+            gp[torch.arange(bl), off + torch.arange(bl)] -= KAPPA * cps[p]  # the identity term, before the fp16 rounding
+            g[p, :, :bg] = gp.half()
 
     def _gprime(self, ws):
         bl, bg, d, off = self._dims(ws)
@@ -229,11 +231,6 @@ class EmulatedBackend:
         dots = []
         for m, (x, out) in enumerate(zip((img, txt, aud), (dimg, dtxt, daud))):
             dd = row_out[m] + (col[m].double() if col is not None else 0.0)
-            if stashed:  # the "- kappa c_p I" term of G' that the scaled stash does not carry
-                m1, m2 = (m + 1) % 3, (m + 2) % 3
-                k1 = math.exp(float(t3[m])) * float(g3[m]) / bg
-                k2 = math.exp(float(t3[m2])) * float(g3[m2]) / bg
-                dd = dd - k1 * xh16[m1] - k2 * xh16[m2]
             xh = x.double() * inv[m][:, None]
             dots.append(float((xh * dd).sum()))
             dx = (dd - xh * (xh * dd).sum(-1, keepdim=True)) * inv[m][:, None] * mult

@@ -60,8 +60,8 @@ def test_stash_and_recompute_backwards_agree(b, d, t):
     t3d = torch.tensor(t3, dtype=torch.float32, device="cuda")
     g3d = torch.tensor(g3, dtype=torch.float32, device="cuda")
     res = {}
-    for stash in (True, "hbm_pass", False):
-        cfg = ops.TriContrastiveConfig(math="f16", grads_fp32=True, stash=bool(stash), fuse_scale=stash is True)
+    for stash in (True, False):
+        cfg = ops.TriContrastiveConfig(math="f16", grads_fp32=True, stash=stash)
         res[stash] = ops.forward_backward_raw(*ten, t3d, g3d, cfg)
         torch.cuda.synchronize()
         loss3, dimg, dtxt, daud, dt3 = res[stash]
@@ -71,8 +71,7 @@ def test_stash_and_recompute_backwards_agree(b, d, t):
         assert np.max(np.abs(dt3.cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"])) < TOL_F16
     assert torch.equal(res[True][0], res[False][0])  # identical forward statistics
     assert golden_util.rel(res[True][1].cpu().numpy(), res[False][1].cpu().numpy()) < 5e-4
-    # converting the stash inside the GEMM or in a separate pass rounds the same products to fp16
-    assert golden_util.rel(res[True][1].cpu().numpy(), res["hbm_pass"][1].cpu().numpy()) < 1e-5
+
 
 
 def test_autograd_matches_oracle_and_respects_weights():
@@ -179,3 +178,51 @@ def test_cosine_logits_match_reference_expression(m, n, d, dtype_name, math_mode
     assert got.shape == (m, n)
     err = ((got - want) ** 2).sum().sqrt() / (want ** 2).sum().sqrt()
     assert err < tol, err
+
+
+@pytest.mark.parametrize("b,d,dtype_name,math_mode,stash,tol", [
+    (300, 768, "bfloat16", "f16", True, TOL_F16),
+    (520, 512, "bfloat16", "f16", False, TOL_F16),
+    (200, 256, "float32", "f16x3", False, TOL_F32),
+])
+def test_mixed_temperatures_split_the_pairs_between_the_two_forward_kernels(b, d, dtype_name, math_mode, stash, tol):
+    """The scales are read on the device: pairs with s < 44 take the folded-exponent epilogue (forward_fast_kernel), the
+    others the per-tile-maximum one (forward_tiles_kernel), in the same forward.  One pair of each kind plus one just
+    below the switch."""
+    from synergy_clip_b200 import ops
+
+    dtype = getattr(torch, dtype_name)
+    embs = closed_form.synthetic_embeddings(b, d, 77, 0.12)
+    if dtype == torch.bfloat16:
+        embs = [closed_form.round_to_bf16(e) for e in embs]
+    t3, g3 = (2.6592, math.log(43.5), math.log(100.0)), (0.5, 1.0, 0.25)
+    want = closed_form.tri_contrastive(*embs, t3, g3)
+    ten = [torch.from_numpy(e).cuda().to(dtype) for e in embs]
+    cfg = ops.TriContrastiveConfig(math=math_mode, grads_fp32=True, stash=stash)
+    loss3, dimg, dtxt, daud, dt3 = ops.forward_backward_raw(
+        *ten, torch.tensor(t3, dtype=torch.float32, device="cuda"), torch.tensor(g3, dtype=torch.float32, device="cuda"),
+        cfg)
+    assert np.max(np.abs(loss3.double().cpu().numpy() - want["loss"]) / want["loss"]) < tol
+    for got, key in ((dimg, "dimg"), (dtxt, "dtxt"), (daud, "daud")):
+        assert golden_util.rel(got.double().cpu().numpy(), want[key]) < tol, key
+    assert np.max(np.abs(dt3.double().cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"])) < tol
+
+
+@pytest.mark.parametrize("t", [2.6592, math.log(43.5)])
+def test_peaked_softmax_keeps_gradient_precision_on_the_stash_path(t):
+    """A trained-like batch (positive-pair cosine 0.25): the positive-pair entry of G' is kappa c_p (P_ii - 1), a small
+    difference.  The conversion pass subtracts the identity in fp32 before the fp16 rounding, so the stash path stays
+    inside the tolerance where it used to lose it (1.7e-3 at s = 43.5 with the identity applied behind the GEMM)."""
+    from synergy_clip_b200 import ops
+
+    b, d = 300, 768
+    embs = [closed_form.round_to_bf16(e) for e in closed_form.synthetic_embeddings(b, d, 77, 0.25)]
+    t3, g3 = (t, t, t), (0.5, 1.0, 0.25)
+    want = closed_form.tri_contrastive(*embs, t3, g3)
+    ten = [torch.from_numpy(e).cuda().bfloat16() for e in embs]
+    out = ops.forward_backward_raw(*ten, torch.tensor(t3, dtype=torch.float32, device="cuda"),
+                                   torch.tensor(g3, dtype=torch.float32, device="cuda"),
+                                   ops.TriContrastiveConfig(math="f16", grads_fp32=True, stash=True))
+    for got, key in zip(out[1:4], ("dimg", "dtxt", "daud")):
+        assert golden_util.rel(got.double().cpu().numpy(), want[key]) < TOL_F16, key
+    assert np.max(np.abs(out[4].double().cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"])) < TOL_F16

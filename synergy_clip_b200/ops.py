@@ -185,6 +185,34 @@ class _SymmWorkspace(_Workspace):
         self.group = group
 
 
+_P2P_FAILED = False
+
+
+def _try_symm_workspace(pb: Problem, device, group):
+    """Symmetric-memory workspace, or None when the platform refuses it (no peer mapping between these GPUs, handle
+    exchange not permitted, ...).  The decision is taken by all ranks together -- a rank-local fallback would leave the
+    others waiting in a barrier -- and is sticky: after one failure the NCCL transport is used for good."""
+    global _P2P_FAILED
+    import torch.distributed as dist
+
+    if _P2P_FAILED:
+        return None
+    ws, err = None, None
+    try:
+        ws = _SymmWorkspace(pb, device, group)
+    except Exception as e:  # noqa: BLE001
+        err = e
+    ok = torch.tensor([0 if ws is None else 1], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        return ws
+    _P2P_FAILED = True
+    import warnings
+
+    warnings.warn(f"symmetric-memory workspace unavailable ({err!r}); the sharded path uses NCCL collectives instead")
+    return None
+
+
 def _symm_available() -> bool:
     try:
         import torch.distributed._symmetric_memory as symm  # noqa: F401
@@ -222,12 +250,20 @@ class _Pool:
             if lst:
                 return lst.pop()
         if symm_group is not None:
-            return _SymmWorkspace(pb, device, symm_group)
+            ws = _try_symm_workspace(pb, device, symm_group)
+            if ws is not None:
+                return ws
         return _Workspace(pb, device)
 
     def release(self, ws: _Workspace):
         with self._lock:
             self._free.setdefault(self._key(ws.pb, ws.blob.device, getattr(ws, "group", None)), []).append(ws)
+
+    def acquire_sharded(self, pb: Problem, device, group, want_p2p: bool) -> _Workspace:
+        """Sharded problems: a symmetric-memory workspace when the peer-memory transport is wanted and available."""
+        if want_p2p and not _P2P_FAILED:
+            return self.acquire(pb, device, group)
+        return self.acquire(pb, device, None)
 
     def clear(self):
         with self._lock:
@@ -639,7 +675,7 @@ class _TriContrastive(torch.autograd.Function):
     def forward(ctx, img, txt, aud, t3, cfg):
         img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
         pb, _, _ = _make_problem(img, cfg)
-        ws = _POOL.acquire(pb, img.device, cfg.process_group if _use_p2p(cfg, img) else None)
+        ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
         lease = _Lease(ws)
         loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         ctx.save_for_backward(img, txt, aud, t3)
@@ -675,7 +711,7 @@ def fused_tri_contrastive(img: torch.Tensor, txt: torch.Tensor, aud: torch.Tenso
     else:  # eval loops run under torch.no_grad() (main_pretraining.py:192-210): nothing is kept for backward
         img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
         pb, _, _ = _make_problem(img, cfg)
-        ws = _POOL.acquire(pb, img.device, cfg.process_group if _use_p2p(cfg, img) else None)
+        ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
         try:
             loss3 = _forward_impl(ws, img.detach(), txt.detach(), aud.detach(), t3.detach(), cfg)
         finally:
@@ -688,7 +724,7 @@ def forward_backward_raw(img, txt, aud, t3, g3, config: Optional[TriContrastiveC
     cfg = config or _DEFAULT
     _check_inputs(img, txt, aud)
     pb, _, _ = _make_problem(img, cfg)
-    ws = _POOL.acquire(pb, img.device, cfg.process_group if _use_p2p(cfg, img) else None)
+    ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
     try:
         loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, cfg)

@@ -226,3 +226,22 @@ def test_peaked_softmax_keeps_gradient_precision_on_the_stash_path(t):
     for got, key in zip(out[1:4], ("dimg", "dtxt", "daud")):
         assert golden_util.rel(got.double().cpu().numpy(), want[key]) < TOL_F16, key
     assert np.max(np.abs(out[4].double().cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"])) < TOL_F16
+
+
+@pytest.mark.parametrize("b,d,stash", [(200, 520, True), (200, 520, False), (130, 72, True), (260, 1096, True)])
+def test_dims_that_are_not_multiples_of_the_tile_sizes(b, d, stash):
+    """dim only has to be a multiple of 8 (16-byte rows for TMA): partial k blocks of the similarity tiles, partial n
+    tiles of the 384 / 512-column gradient GEMM tiles and ragged row tiles are all zero-filled by the tensor maps."""
+    from synergy_clip_b200 import ops
+
+    embs = [closed_form.round_to_bf16(e) for e in closed_form.synthetic_embeddings(b, d, 3, 0.1)]
+    t3, g3 = (2.6592, 2.4, 2.9), (1.0, 0.5, 0.25)
+    want = closed_form.tri_contrastive(*embs, t3, g3)
+    ten = [torch.from_numpy(e).cuda().bfloat16() for e in embs]
+    out = ops.forward_backward_raw(*ten, torch.tensor(t3, dtype=torch.float32, device="cuda"),
+                                   torch.tensor(g3, dtype=torch.float32, device="cuda"),
+                                   ops.TriContrastiveConfig(math="f16", grads_fp32=True, stash=stash))
+    assert np.max(np.abs(out[0].double().cpu().numpy() - want["loss"]) / want["loss"]) < TOL_F16
+    for got, key in zip(out[1:4], ("dimg", "dtxt", "daud")):
+        assert golden_util.rel(got.double().cpu().numpy(), want[key]) < TOL_F16, key
+    assert np.max(np.abs(out[4].double().cpu().numpy() - want["dscale"])) / np.max(np.abs(want["dscale"])) < TOL_F16

@@ -104,3 +104,74 @@ def test_single_rank_emulation_matches_oracle():
             assert np.sqrt(((g - want[key]) ** 2).sum() / (want[key] ** 2).sum()) < 2e-6, key
     finally:
         ops._BACKEND = saved
+
+
+# ---- under the caller's DDP wrapper (main_pretraining.py:138): hooks fire on the projection heads and the three scales
+class _Heads(torch.nn.Module):
+    """The part of Tri_CLIP that sits on the path: three bias-free projection heads (model.py:76-78) and the three
+    log-temperatures (model.py:80-82), fed with pooled features instead of encoders."""
+
+    def __init__(self, hidden, dim, cfg):
+        super().__init__()
+        self.vision_projection = torch.nn.Linear(hidden, dim, bias=False)
+        self.text_projection = torch.nn.Linear(hidden, dim, bias=False)
+        self.audio_projection = torch.nn.Linear(hidden, dim, bias=False)
+        self.logit_scale_for_IT = torch.nn.Parameter(torch.tensor(2.6592))
+        self.logit_scale_for_TA = torch.nn.Parameter(torch.tensor(2.6592))
+        self.logit_scale_for_AI = torch.nn.Parameter(torch.tensor(2.6592))
+        self.cfg = cfg
+
+    def forward(self, pv, pt, pa):
+        from synergy_clip_b200 import fused_tri_contrastive
+
+        return fused_tri_contrastive(self.vision_projection(pv), self.text_projection(pt), self.audio_projection(pa),
+                                     self.logit_scale_for_IT, self.logit_scale_for_TA, self.logit_scale_for_AI,
+                                     config=self.cfg)
+
+
+def _ddp_worker(rank, world, port, rows_local, hidden, dim, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from synergy_clip_b200 import ops
+        from tests.emulated_backend import EmulatedBackend
+
+        ops._BACKEND = EmulatedBackend()
+        torch.manual_seed(11)  # same weights on every rank
+        cfg = ops.TriContrastiveConfig(process_group=dist.group.WORLD, math="f16x3", grad_scale="ddp")
+        model = torch.nn.parallel.DistributedDataParallel(_Heads(hidden, dim, cfg))
+        g = torch.Generator().manual_seed(5)
+        pooled = [torch.randn(rows_local * world, hidden, generator=g) for _ in range(3)]
+        sl = slice(rank * rows_local, (rank + 1) * rows_local)
+        it, ta, ai = model(*[p[sl] for p in pooled])
+        (it * W3[0] + ta * W3[1] + ai * W3[2]).backward()  # DDP's hooks average the parameter gradients over ranks
+        torch.save({k: p.grad.clone() for k, p in model.module.named_parameters()},
+                   os.path.join(out_dir, f"ddp{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_wrapper_averages_to_the_global_batch_gradient(tmp_path):
+    """With grad_scale="ddp" every rank hands W x its partial derivative to autograd, so DDP's mean over ranks is the
+    exact gradient of the global-batch losses with respect to the shared parameters."""
+    from oracle import reference_tail
+
+    rows_local, hidden, dim = 48, 24, 32
+    mp.spawn(_ddp_worker, args=(WORLD, _free_port(), rows_local, hidden, dim, str(tmp_path)), nprocs=WORLD, join=True)
+    grads = [torch.load(tmp_path / f"ddp{r}.pt") for r in range(WORLD)]
+    for k in grads[0]:  # after the all-reduce every rank holds the same averaged gradient
+        assert torch.allclose(grads[0][k], grads[1][k], rtol=1e-6, atol=1e-9), k
+    # single-process truth: the reference tail (autograd, fp64) on the whole batch through the same heads
+    torch.manual_seed(11)
+    ref = _Heads(hidden, dim, None).double()
+    g = torch.Generator().manual_seed(5)
+    pooled = [torch.randn(rows_local * WORLD, hidden, generator=g).double() for _ in range(3)]
+    losses = reference_tail.tail_losses(ref.vision_projection(pooled[0]), ref.text_projection(pooled[1]),
+                                        ref.audio_projection(pooled[2]), ref.logit_scale_for_IT,
+                                        ref.logit_scale_for_TA, ref.logit_scale_for_AI)
+    sum(w * l for w, l in zip(W3, losses)).backward()
+    for k, p in ref.named_parameters():
+        want, got = p.grad, grads[0][k].double()
+        err = (got - want).norm() / want.norm()
+        assert err < 1e-5, (k, float(err))

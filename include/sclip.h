@@ -162,21 +162,13 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
  * precision when the softmax is sharply peaked.  HBM-bound elementwise pass. */
 int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
-/* Only the factor vectors R1, R2, C1, C2 of that conversion (round-1 experiment: with sclip_backward_gemms_role and
- * SCLIP_BWD_STASHED the gradient GEMMs convert the stashed tiles in shared memory on their way to the tensor cores --
- * measured slower than the HBM pass, and WITHOUT the identity term, which that experiment applied separately; not used
- * by the Python op). */
-int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
-
 /* dxhat_row[m] = G'_{rowpair(m)} . xhat_{col modality}   (rows_local x dim, complete)
  * dxhat_col[m] = G'_{colpair(m)}^T . xhat_{row modality} (rows_global x dim partial sums; world == 1: added
  *                into dxhat_row by the same accumulator instead). */
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
-/* Same, one role at a time (world > 1): SCLIP_ROLE_COLUMN writes only dxhat_col (so its reduce-scatter can start),
- * SCLIP_ROLE_ROW only dxhat_row; SCLIP_ROLE_BOTH == sclip_backward_gemms.
- * flags & SCLIP_BWD_STASHED: grad_tiles still holds the raw stash of the forward (sclip_backward_factors has run,
- * sclip_backward_scale has not): every A tile is multiplied by (R1_i C1_j + R2_i C2_j) in shared memory. */
+/* Same, one role at a time (world > 1): SCLIP_ROLE_COLUMN writes only dxhat_col (so its exchange can start),
+ * SCLIP_ROLE_ROW only dxhat_row; SCLIP_ROLE_BOTH == sclip_backward_gemms.  flags: reserved, pass 0. */
 #define SCLIP_ROLE_BOTH 0
 #define SCLIP_ROLE_COLUMN 1
 #define SCLIP_ROLE_ROW 2

@@ -54,7 +54,6 @@ _PROTOTYPES = {
     "sclip_backward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_gemms": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_gemms_role": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "sclip_backward_factors": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_set_max_sms": (c_int, [c_int]),
     "sclip_backward_finish": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -18,8 +18,7 @@ constexpr int BK = 64;       // fp16 elements per k block = one 128-byte swizzle
 constexpr int UMMA_K = 16;   // k extent of one tcgen05.mma kind::f16
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KiB
-constexpr int KVEC_BYTES = 1024;             // per stage: two 64-float k-side factor vectors (512 B used)
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES + KVEC_BYTES;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int MN_BOX_BYTES = 64 * BK * 2;    // one 64(mn) x 64(k) box of an MN-major operand
 
 constexpr float kKappa = 32768.0f;           // scale of the fp16 softmax-gradient tiles (|G'| <= kappa)
@@ -43,11 +42,6 @@ struct Segment {
   int a_mn;    // 0: operand stored [rows][k] (K-major)   1: stored [k][rows] (MN-major)
   int b_mn;
   int num_kb;  // number of BK-wide k blocks
-  // transform != 0: the A tiles are converted in shared memory before the MMA reads them,
-  //   A(m, k) <- A(m, k) * (um[m] * wk[k] + um2[m] * wk2[k]),
-  // with the four factor vectors at these float offsets from GemmParams::fac (k vectors padded to 64 floats)
-  int transform;
-  int um_off, um2_off, wk_off, wk2_off;
   int map_a64;  // K-major A operand with a 64-row box (multicast halves of the wide GEMM tiles); -1 if unused
 };
 
@@ -169,7 +163,6 @@ struct GemmParams {
   int total_tiles;
   int stages;
   int wn;            // wide kernel: accumulator columns of one CTA-pair tile (256 | 384 | 512)
-  const float* fac;  // base of the conversion factor vectors (Segment::transform)
   const float* t3;   // when non-null alpha = alpha0 * max_q |exp(t_q) g_q| (backward); else alpha = alpha0
   const float* g3;
   const float* log_alpha;  // when non-null alpha is further multiplied by exp(*log_alpha) (zero-shot scorers)
@@ -205,6 +198,6 @@ int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first
 int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, cudaStream_t stream);
 int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t src_off, int count, float* out,
                       bool sum_loss, cudaStream_t stream);
-int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, bool factors_only, cudaStream_t stream);
+int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream);
 
 }  // namespace sclip

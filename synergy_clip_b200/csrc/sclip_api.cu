@@ -336,7 +336,7 @@ struct MapTable {
 };
 
 Segment seg(int a, int b, int a_mn, int b_mn, int num_kb, int a64 = -1) {
-  return Segment{a, b, a_mn, b_mn, num_kb, 0, 0, 0, 0, 0, a64};
+  return Segment{a, b, a_mn, b_mn, num_kb, a64};
 }
 
 // similarity job of pair p (forward and the backward recompute)
@@ -414,18 +414,7 @@ int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3
     set_error("sclip_backward_scale needs t3, g3 and a SCLIP_MATH_F16 problem");
     return SCLIP_ERR_ARGUMENT;
   }
-  return launch_backward_scale(w, t3, g3, false, static_cast<cudaStream_t>(stream));
-}
-
-int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
-  Workspace w;
-  int rc = resolve(problem, ws, &w);
-  if (rc) return rc;
-  if (t3 == nullptr || g3 == nullptr || w.pb.math != SCLIP_MATH_F16) {
-    set_error("sclip_backward_factors needs t3, g3 and a SCLIP_MATH_F16 problem");
-    return SCLIP_ERR_ARGUMENT;
-  }
-  return launch_backward_scale(w, t3, g3, true, static_cast<cudaStream_t>(stream));
+  return launch_backward_scale(w, t3, g3, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
@@ -569,26 +558,7 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
     if (do_col) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
   }
   int nj = 0, tiles = 0;
-  const bool convert = (flags & SCLIP_BWD_STASHED) != 0;
-  if (convert && x3) {
-    set_error("SCLIP_BWD_STASHED is only defined for SCLIP_MATH_F16");
-    return SCLIP_ERR_ARGUMENT;
-  }
-  p.fac = w.fac_row;
-  const int ld_row = static_cast<int>(align_up(bl, 64)), ld_col = static_cast<int>(align_up(bg, 64));
-  const int col_base = static_cast<int>(w.fac_col - w.fac_row);  // float offset of fac_col from fac_row
-  auto conv = [&](Segment sgm, int pair, bool row_role) {
-    if (!convert) return sgm;
-    const int r1 = (pair * 2 + 0) * ld_row, r2 = (pair * 2 + 1) * ld_row;
-    const int c1 = col_base + (pair * 2 + 0) * ld_col, c2 = col_base + (pair * 2 + 1) * ld_col;
-    sgm.transform = 1;
-    if (row_role) {  // A = stash (m = local row i, k = global column j): F = R1_i C1_j + R2_i C2_j
-      sgm.um_off = r1; sgm.um2_off = r2; sgm.wk_off = c1; sgm.wk2_off = c2;
-    } else {         // A = stash^T (m = global column j, k = local row i)
-      sgm.um_off = c1; sgm.um2_off = c2; sgm.wk_off = r1; sgm.wk2_off = r2;
-    }
-    return sgm;
-  };
+  (void)flags;  // reserved (round 1 used a bit for the in-GEMM stash conversion experiment, commit 5c56fe2)
   auto add_role = [&](Job& job, int m, bool row_role) {
     if (row_role) {  // G'_{pair m} (rows_local x rows_global, K-major) . xhat_{col modality} (k = global row)
       const int pr = modality_row_pair(m), cm = pair_col_modality(pr);
@@ -597,14 +567,14 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
         job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
       }
       // (the 64 x 64 box map of the MN-major view doubles as the 64-row K-major box of the multicast halves)
-      job.seg[job.nseg++] = conv(seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g, tab.use(kGMN + pr)), pr, true);
+      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g, tab.use(kGMN + pr));
     } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
       const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
       if (x3) {
         job.seg[job.nseg++] = seg(tab.use(kGloMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
         job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXloLocMN + rm), 1, 1, kb_l);
       }
-      job.seg[job.nseg++] = conv(seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l), pc, false);
+      job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
     }
   };
   for (int m = 0; m < 3 && do_row; ++m) {
@@ -640,7 +610,7 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
   }
   if (tab.rc) return tab.rc;
   p.njobs = nj;
-  if (wide_enabled() && !x3 && !convert) {
+  if (wide_enabled() && !x3) {
     // 256 x wn tiles, k split so that the clusters finish together; split partial sums are added into zeroed outputs
     p.wn = wide_width(pb.dim);
     int kb_max = 0, base_tiles = 0;
@@ -892,7 +862,7 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
     rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN / cta_group());
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK), 0, 0, 0, 0, 0, 2};
+  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK), 2};
   if (!a_mn) rc = make_map(&p.maps[2], a, k, m, lda, BK, 64);  // 64-row boxes (multicast halves of the wide tiles)
   if (rc) return rc;
   p.jobs[0].nseg = 1;

@@ -737,14 +737,13 @@ int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream) {
   return SCLIP_OK;
 }
 
-int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, bool factors_only, cudaStream_t stream) {
+int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
   const int ld_row = (w.pb.rows_local + 63) / 64 * 64, ld_col = (w.pb.rows_global + 63) / 64 * 64;
   FactorArgs f{t3, g3, w.diag_all, w.lse_row, w.lse_col, w.fac_row, w.fac_col,
                w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, ld_row, ld_col};
   const int n = ld_row > ld_col ? ld_row : ld_col;
   backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
   SCLIP_LAUNCHED();
-  if (factors_only) return SCLIP_OK;
   ScaleArgs a{w.g[0], w.fac_row, w.fac_col, t3, g3, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col,
               w.pb.row_offset};
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);

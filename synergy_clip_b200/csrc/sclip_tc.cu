@@ -27,13 +27,10 @@ namespace {
 constexpr int kMaxStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kMaxEpiWarps = 16;
-constexpr int kConvGroups = 4;   // groups of epilogue warps that take the conversion k blocks round-robin
 
 struct __align__(8) PipeBarriers {
   uint64_t full[kMaxStages];    // TMA -> MMA: operand bytes have landed (leader CTA's barrier collects both CTAs' bytes)
   uint64_t empty[kMaxStages];   // MMA -> TMA: the MMAs that read this slot have completed
-  uint64_t afull[kMaxStages];   // conversion segments: this CTA's own A tile + k factors have landed
-  uint64_t ready[kMaxStages];   // conversion segments: all CG * EW warps have converted their part of the A tile
   uint64_t tmem_full[kAccStages];
   uint64_t tmem_empty[kAccStages];
   uint32_t tmem_base;
@@ -44,7 +41,7 @@ template <int CG>
 struct Geo {
   static constexpr int kBRows = BN / CG;                               // B rows loaded by one CTA per stage
   static constexpr int kBBytes = kBRows * BK * 2;
-  static constexpr int kStageBytes = A_STAGE_BYTES + kBBytes + KVEC_BYTES;  // 49 KiB (CG 1) / 33 KiB (CG 2)
+  static constexpr int kStageBytes = A_STAGE_BYTES + kBBytes;               // 48 KiB (CG 1) / 32 KiB (CG 2)
   static constexpr int kLoadBytes = A_STAGE_BYTES + kBBytes;                // bytes the tensor loads deliver
   static constexpr int kTileM = BM * CG;                               // rows of one cluster tile
 };
@@ -68,15 +65,12 @@ struct Tile {
 struct RingState {
   int stage = 0;
   uint32_t phase = 0;
-  uint32_t tpar = 0;  // per stage: parity of the number of conversion k blocks that used it (afull / ready phases)
   __device__ __forceinline__ void advance(int stages) {
     if (++stage == stages) {
       stage = 0;
       phase ^= 1u;
     }
   }
-  __device__ __forceinline__ uint32_t conv_parity() const { return (tpar >> stage) & 1u; }
-  __device__ __forceinline__ void conv_used() { tpar ^= 1u << stage; }
 };
 
 // k blocks [lo, hi) of a segment handled by split `split` of `ksplits`
@@ -88,8 +82,7 @@ __device__ __forceinline__ void split_range(int num_kb, int split, int ksplits, 
 // ---------------------------------------------------------------------------------------------- mainloop roles
 template <int CG>
 __device__ __forceinline__ void producer_tile(const CUtensorMap* maps, const Job& job, const Tile& t, uint32_t rank,
-                                              uint8_t* smem, PipeBarriers* bars, int stages, RingState& rs,
-                                              const float* fac = nullptr) {
+                                              uint8_t* smem, PipeBarriers* bars, int stages, RingState& rs) {
   using G = Geo<CG>;
   const int m0 = t.m0 + static_cast<int>(rank) * BM;         // this CTA's accumulator rows
   const int n0 = t.n0 + static_cast<int>(rank) * G::kBRows;  // this CTA's share of the B rows
@@ -104,43 +97,6 @@ __device__ __forceinline__ void producer_tile(const CUtensorMap* maps, const Job
       uint8_t* sa = smem + rs.stage * G::kStageBytes;
       uint8_t* sb = sa + A_STAGE_BYTES;
       const int k = kb * BK;
-      if (seg.transform) {
-        // A tile and the k-side factors go to this CTA's own barrier (its warps convert the tile in place); the B
-        // tile goes to the MMA issuer's barrier as usual
-        uint64_t* abar = &bars->afull[rs.stage];
-        mbar_expect_tx(abar, A_STAGE_BYTES + 512);
-        if (!seg.a_mn) {
-          tma_load_2d(sa, ma, abar, k, m0);
-        } else {
-#pragma unroll
-          for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * MN_BOX_BYTES, ma, abar, m0 + g * 64, k);
-        }
-        uint8_t* kv = sb + G::kBBytes;
-        bulk_load_1d(kv, fac + seg.wk_off + k, 256, abar);
-        bulk_load_1d(kv + 256, fac + seg.wk2_off + k, 256, abar);
-        if constexpr (CG == 1) {
-          uint64_t* bar = &bars->full[rs.stage];
-          mbar_expect_tx(bar, G::kBBytes);
-          if (!seg.b_mn) {
-            tma_load_2d(sb, mb, bar, k, n0);
-          } else {
-#pragma unroll
-            for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
-          }
-        } else {
-          const uint32_t bar = mapa(smem_u32(&bars->full[rs.stage]), 0);
-          if (rank == 0) mbar_expect_tx(&bars->full[rs.stage], CG * G::kBBytes);
-          if (!seg.b_mn) {
-            tma_load_2d_2sm(sb, mb, bar, k, n0);
-          } else {
-#pragma unroll
-            for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d_2sm(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
-          }
-        }
-        rs.conv_used();
-        rs.advance(stages);
-        continue;
-      }
       if constexpr (CG == 1) {
         uint64_t* bar = &bars->full[rs.stage];
         mbar_expect_tx(bar, G::kLoadBytes);
@@ -193,10 +149,6 @@ __device__ __forceinline__ void mma_tile(const Job& job, const Tile& t, uint8_t*
     split_range(seg.num_kb, t.split, job.ksplits, kb_lo, kb_hi);
     for (int kb = kb_lo; kb < kb_hi; ++kb) {
       mbar_wait_bounded<false>(&bars->full[rs.stage], rs.phase, 2);
-      if (seg.transform) {  // the A tile of this slot has been converted by all epilogue warps (of both CTAs)
-        mbar_wait_bounded<false>(&bars->ready[rs.stage], rs.conv_parity(), 5);
-        rs.conv_used();
-      }
       tc_fence_after();
       const uint32_t a_base = smem_u32(smem + rs.stage * G::kStageBytes);
       const uint32_t b_base = a_base + A_STAGE_BYTES;
@@ -229,8 +181,6 @@ __device__ __forceinline__ uint32_t kernel_setup(PipeBarriers* bars, int warp, i
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
-      mbar_init(&bars->afull[i], 1);
-      mbar_init(&bars->ready[i], CG * (EW / kConvGroups));
     }
 #pragma unroll
     for (int i = 0; i < kAccStages; ++i) {
@@ -1220,88 +1170,6 @@ __device__ __forceinline__ Tile decode_gemm(const GemmParams& P, int t) {
   return r;
 }
 
-// In-place conversion of one A tile (16 KiB, fp16, 128-byte swizzle) by the EW epilogue warps of a CTA:
-//   A(m, k) <- A(m, k) * (um[m] * wk[k] + um2[m] * wk2[k])
-// The tile is 1024 16-byte chunks; thread `tid` of the NT that share a tile handles chunks tid + NT u.  Its chunk column c = tid & 7
-// is the same for every u, so for a K-major tile (rows = m, chunk = 8 consecutive k) the k factors are fixed per
-// thread and the m factors vary with u; for an MN-major tile (rows = k, two 64-wide m boxes, chunk = 8 consecutive m)
-// it is the other way round.
-template <int NT>                          // threads that share one tile: 64 .. 512
-struct TileConverter {
-  static constexpr int CPT = 1024 / NT;   // chunks per thread
-  float fm[16], fm2[16];                  // m-side factors: K-major: [u] ; MN-major: [box][e]
-
-  __device__ __forceinline__ void load_m(const float* um, const float* um2, int m0, int m_limit, int tid, bool a_mn) {
-    if (!a_mn) {
-#pragma unroll
-      for (int u = 0; u < CPT; ++u) {
-        const int m = m0 + (tid >> 3) + (NT >> 3) * u;
-        fm[u] = m < m_limit ? um[m] : 0.f;
-        fm2[u] = m < m_limit ? um2[m] : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int m = m0 + 64 * g + 8 * (tid & 7) + e;
-          fm[8 * g + e] = m < m_limit ? um[m] : 0.f;
-          fm2[8 * g + e] = m < m_limit ? um2[m] : 0.f;
-        }
-    }
-  }
-
-  __device__ __forceinline__ void convert(uint8_t* a_tile, const float* kvec, int tid, bool a_mn) const {
-    const int c = tid & 7;
-    if (!a_mn) {
-      float wk[8], wk2[8];
-#pragma unroll
-      for (int e = 0; e < 8; e += 4) {
-        const float4 f = *reinterpret_cast<const float4*>(kvec + 8 * c + e);
-        const float4 f2 = *reinterpret_cast<const float4*>(kvec + 64 + 8 * c + e);
-        wk[e] = f.x; wk[e + 1] = f.y; wk[e + 2] = f.z; wk[e + 3] = f.w;
-        wk2[e] = f2.x; wk2[e + 1] = f2.y; wk2[e + 2] = f2.z; wk2[e + 3] = f2.w;
-      }
-#pragma unroll
-      for (int u = 0; u < CPT; ++u) {
-        const int r = (tid >> 3) + (NT >> 3) * u;
-        uint4* ptr = reinterpret_cast<uint4*>(a_tile + r * 128 + ((c ^ (r & 7)) << 4));
-        uint4 w = *ptr;
-        __half2* h = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 x = __half22float2(h[e]);
-          x.x *= fmaf(fm[u], wk[2 * e], fm2[u] * wk2[2 * e]);
-          x.y *= fmaf(fm[u], wk[2 * e + 1], fm2[u] * wk2[2 * e + 1]);
-          h[e] = __floats2half2_rn(x.x, x.y);
-        }
-        *ptr = w;
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < CPT; ++u) {
-        const int q = tid + NT * u;
-        const int g = q >> 9;            // 64-wide m box
-        const int krow = (q >> 3) & 63;  // k row inside the box
-        const float wk = kvec[krow], wk2 = kvec[64 + krow];
-        uint4* ptr = reinterpret_cast<uint4*>(a_tile + g * MN_BOX_BYTES + krow * 128 + ((c ^ (krow & 7)) << 4));
-        uint4 w = *ptr;
-        __half2* h = reinterpret_cast<__half2*>(&w);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float2 x = __half22float2(h[e]);
-          // the box index (NT u) >> 9 is a compile-time constant after unrolling
-          const int o = 8 * ((NT * u) >> 9) + 2 * e;
-          x.x *= fmaf(fm[o], wk, fm2[o] * wk2);
-          x.y *= fmaf(fm[o + 1], wk, fm2[o + 1] * wk2);
-          h[e] = __floats2half2_rn(x.x, x.y);
-        }
-        *ptr = w;
-      }
-    }
-  }
-};
-
 template <int CG, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __grid_constant__ GemmParams P) {
   constexpr int S = EW / 4;
@@ -1322,7 +1190,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
       RingState rs;
       for (int t = cluster_id; t < total; t += num_clusters) {
         const Tile tile = decode_gemm<CG>(P, t);
-        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs, P.fac);
+        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
       }
     }
     __syncwarp();
@@ -1349,8 +1217,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
     }
     if (P.log_alpha != nullptr) alpha *= expf(*P.log_alpha);  // a learnable log-temperature read on the device
     int it = 0;
-    RingState conv_ring;
-    uint32_t conv_count = 0;
     for (int t = cluster_id; t < total; t += num_clusters, ++it) {
       const Tile tile = decode_gemm<CG>(P, t);
       const int acc = it & 1;
@@ -1362,43 +1228,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
       const int c0 = tile.n0 + slice * CS;
       float* out = P.out[j] + static_cast<size_t>(row) * P.ldc[j] + c0;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + slice * CS;
-      {
-        // conversion segments: follow the producer's ring and convert this CTA's A tile in place (stash -> G', see
-        // backward_scale_kernel) before the MMA issuer may read it.  The warps form kConvGroups groups that take the
-        // k blocks round-robin, so the fixed per-block cost (barrier wait, proxy fence, arrive) is paid by EW /
-        // kConvGroups warps per block instead of all EW.
-        const Job& job = P.jobs[j];
-        constexpr int kGroupWarps = EW / kConvGroups;
-        const int group = warp / kGroupWarps;
-        const int tid = (warp % kGroupWarps) * 32 + lane;
-        const int m0_cta = tile.m0 + static_cast<int>(rank) * BM;
-        for (int sg = 0; sg < job.nseg; ++sg) {
-          const Segment seg = job.seg[sg];
-          int kb_lo, kb_hi;
-          split_range(seg.num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
-          if (!seg.transform) {
-            for (int kb = kb_lo; kb < kb_hi; ++kb) conv_ring.advance(P.stages);
-            continue;
-          }
-          TileConverter<32 * kGroupWarps> cv;
-          cv.load_m(P.fac + seg.um_off, P.fac + seg.um2_off, m0_cta, P.m[j], tid, seg.a_mn != 0);
-          for (int kb = kb_lo; kb < kb_hi; ++kb, ++conv_count) {
-            if (conv_count % kConvGroups == group) {
-              mbar_wait_bounded<false>(&bars.afull[conv_ring.stage], conv_ring.conv_parity(), 6);
-              uint8_t* sa = smem + conv_ring.stage * Geo<CG>::kStageBytes;
-              cv.convert(sa, reinterpret_cast<const float*>(sa + A_STAGE_BYTES + Geo<CG>::kBBytes), tid, seg.a_mn != 0);
-              fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-              __syncwarp();
-              if (lane == 0) {
-                if (CG == 1 || rank == 0) mbar_arrive(&bars.ready[conv_ring.stage]);
-                else mbar_arrive_cluster(&bars.ready[conv_ring.stage], 0);
-              }
-            }
-            conv_ring.conv_used();
-            conv_ring.advance(P.stages);
-          }
-        }
-      }
       mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
       tc_fence_after();
 #pragma unroll

@@ -361,13 +361,9 @@ class _CudaBackend:
         _lib.check(self.lib.sclip_backward_scale(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
                    "sclip_backward_scale")
 
-    def backward_gemms_role(self, ws, t3, g3, role, convert=False):
-        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role),
-                                                      1 if convert else 0, _stream()), "sclip_backward_gemms_role")
-
-    def backward_factors(self, ws, t3, g3):
-        _lib.check(self.lib.sclip_backward_factors(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
-                   "sclip_backward_factors")
+    def backward_gemms_role(self, ws, t3, g3, role):
+        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), 0,
+                                                      _stream()), "sclip_backward_gemms_role")
 
     def set_max_sms(self, n):
         return self.lib.sclip_set_max_sms(int(n))
@@ -580,11 +576,8 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
     dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
     stashed = bool(getattr(ws, "stashed", False))
-    fused = stashed and cfg.fuse_scale  # convert the stash inside the gradient GEMMs instead of an HBM pass
     _mark("backward_begin")
-    if fused:
-        be.backward_factors(ws, t3, g3)
-    elif stashed:
+    if stashed:
         ws.stashed = False  # converted in place: this stash can serve one backward only
         be.backward_scale(ws, t3, g3)
     else:
@@ -593,7 +586,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     col = None
     mult = 1.0
     if pb.world == 1:
-        be.backward_gemms_role(ws, t3, g3, 0, fused)
+        be.backward_gemms_role(ws, t3, g3, 0)
         _mark("backward_gemms")
     else:
         import torch.distributed as dist
@@ -610,7 +603,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             # (NVLink loads, side stream) while the row-role GEMMs run on the remaining SMs
             cur = torch.cuda.current_stream()
             comm = _comm_stream(img.device)
-            be.backward_gemms_role(ws, t3, g3, 1, fused)
+            be.backward_gemms_role(ws, t3, g3, 1)
             _mark("backward_gemms_col")
             done = torch.cuda.Event()
             done.record(cur)
@@ -629,7 +622,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
                 _LAST_COMM_EVENTS = (_LAST_COMM_EVENTS or []) + [("bwd_barrier", bar_done), ("pull_reduce", reduced)]
             prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms) if cfg.overlap else None
             try:
-                be.backward_gemms_role(ws, t3, g3, 2, fused)
+                be.backward_gemms_role(ws, t3, g3, 2)
             finally:
                 if prev is not None:
                     be.set_max_sms(prev)
@@ -637,14 +630,14 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             cur.wait_event(reduced)
             _mark("backward_gemms")
         elif not (cfg.overlap and img.is_cuda):
-            be.backward_gemms_role(ws, t3, g3, 0, fused)
+            be.backward_gemms_role(ws, t3, g3, 0)
             _mark("backward_gemms")
             scatter()
             _mark("reduce_scatter")
         else:
             cur = torch.cuda.current_stream()
             comm = _comm_stream(img.device)
-            be.backward_gemms_role(ws, t3, g3, 1, fused)  # column role first ...
+            be.backward_gemms_role(ws, t3, g3, 1)  # column role first ...
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(comm):
@@ -654,7 +647,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
                 reduced.record(comm)
             prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
             try:
-                be.backward_gemms_role(ws, t3, g3, 2, fused)
+                be.backward_gemms_role(ws, t3, g3, 2)
             finally:
                 be.set_max_sms(prev)
             cur.wait_event(reduced)

@@ -188,21 +188,10 @@ class EmulatedBackend:
     def set_max_sms(self, n):
         return 0
 
-    def backward_factors(self, ws, t3, g3):
-        pass  # the double recomputes the factors where it needs them
-
     def backward_gemms(self, ws, t3, g3):
         self.backward_gemms_role(ws, t3, g3, 0)
 
-    def backward_gemms_role(self, ws, t3, g3, role, convert=False):
-        if convert:  # the kernels convert the stash tile by tile on its way to the tensor cores; here: out of place
-            lay = ws.lay
-            keep = ws.view(lay.grad_tiles, (3, ws.pb.rows_local, lay.ld_g), torch.float16).clone()
-            self.backward_scale(ws, t3, g3)
-            try:
-                return self.backward_gemms_role(ws, t3, g3, role, False)
-            finally:
-                ws.view(lay.grad_tiles, (3, ws.pb.rows_local, lay.ld_g), torch.float16).copy_(keep)
+    def backward_gemms_role(self, ws, t3, g3, role):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
         mx, _ = self._coeffs(t3, g3)

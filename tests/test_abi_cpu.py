@@ -69,3 +69,23 @@ def test_op_refuses_cpu_tensors():
     t = torch.tensor(2.6592)
     with pytest.raises(_lib.SclipError):
         fused_tri_contrastive(x, x, x, t, t, t)
+
+
+def test_peer_memory_and_scorer_calls_validate_their_arguments():
+    """No device work happens before the argument checks: these run on a machine without a GPU."""
+    lib = _lib.load()
+    need = ctypes.c_uint64()
+    assert lib.sclip_cosine_logits_scratch(0, 10, 512, 0, ctypes.byref(need)) == -1
+    assert lib.sclip_cosine_logits_scratch(128, 1000, 516, 0, ctypes.byref(need)) == -1      # dim not a multiple of 8
+    assert lib.sclip_cosine_logits_scratch(128, 1000, 512, 1, ctypes.byref(need)) == 0
+    assert need.value >= 2 * (128 + 1000) * 512 * 2                                            # hi + lo operand copies
+    assert lib.sclip_cosine_logits(None, None, None, 8, 8, 64, 0, 0, None, None, 8, None) == -1
+    fake_ws = ctypes.c_void_p(1 << 20)                                                         # 256-byte aligned, never touched
+    single = _lib.Problem(128, 128, 0, 512, 1, 0, 1, 0)
+    table = (ctypes.c_void_p * 2)(1 << 20, 2 << 20)
+    assert lib.sclip_pull_shards(ctypes.byref(single), fake_ws, table, 1, 1, 8, None) == -1    # world must be >= 2
+    sharded = _lib.Problem(128, 256, 128, 512, 1, 0, 2, 0)                                     # rank 1 of 2
+    assert lib.sclip_pull_shards(ctypes.byref(sharded), fake_ws, table, 1, 1, 8, None) == -1   # peer_ws[rank] != ws
+    assert b"own workspace" in lib.sclip_last_error()
+    assert lib.sclip_pull_reduce_cols(ctypes.byref(sharded), fake_ws, None, 8, None) == -1
+    assert lib.sclip_kernel_launches() == 0                                                    # nothing was launched

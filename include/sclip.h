@@ -209,9 +209,11 @@ int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, in
 #define SCLIP_MAX_PEERS 16
 
 /* Pull all-gather: copy the normalised operand shards (and their positive-pair logits) of the `count` ranks
- * (rank + first + i) % world, i in [0, count), into this rank's xhat / diag_all.  At most max_blocks thread blocks. */
+ * (rank + first + i) % world, i in [0, count), into this rank's xhat / diag_all.  At most max_blocks thread blocks of
+ * block_threads (<= 1024) threads: either big blocks on SMs left free by sclip_set_max_sms, or 256-thread blocks, one
+ * per SM, which fit beside a resident persistent tile CTA. */
 int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
-                      int max_blocks, void* stream);
+                      int max_blocks, int block_threads, void* stream);
 
 /* col_lse_all[r][3][rows_global] = rank r's lse_col_local (the input of sclip_forward_loss). */
 int sclip_pull_col_lse(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* col_lse_all,
@@ -223,7 +225,7 @@ int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* p
 /* Pull reduce-scatter: col_contrib[m][i][:] = sum over ranks r (rank order) of rank r's dxhat_col[m][row_offset + i][:]
  * -- the column-role gradients of this rank's rows, ready for sclip_backward_finish. */
 int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* const* peer_ws, int max_blocks,
-                           void* stream);
+                           int block_threads /* <= 512 */, void* stream);
 
 /* ---- single-GPU convenience (world == 1): the whole tail in two calls ---------------------------
  * keep_for_backward != 0: sclip_backward will follow on the same workspace (SCLIP_MATH_F16 then stashes in the

@@ -61,10 +61,10 @@ _PROTOTYPES = {
                               c_void_p]),
     "sclip_backward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "sclip_pull_shards": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sclip_pull_shards": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sclip_pull_col_lse": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_pull_loss": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
-    "sclip_pull_reduce_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_void_p]),
+    "sclip_pull_reduce_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "sclip_cosine_logits_scratch": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64)]),
     "sclip_cosine_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                     c_int64, c_void_p]),

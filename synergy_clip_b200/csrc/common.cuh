@@ -194,8 +194,9 @@ int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __
                      cudaStream_t stream);
 // peer-memory exchanges (world > 1, workspaces in symmetric memory); peer_ws[r] = base of rank r's workspace
 int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
+                       int block_threads, cudaStream_t stream);
+int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, int block_threads,
                        cudaStream_t stream);
-int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, cudaStream_t stream);
 int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t src_off, int count, float* out,
                       bool sum_loss, cudaStream_t stream);
 int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream);

@@ -759,8 +759,14 @@ static int check_peers(const Workspace& w, void* ws, const void* const* peer_ws)
   return SCLIP_OK;
 }
 
+static bool bad_block(int block_threads, int limit) {
+  if (block_threads >= 32 && block_threads <= limit && block_threads % 32 == 0) return false;
+  set_error("block_threads=%d must be a multiple of 32 in [32, %d]", block_threads, limit);
+  return true;
+}
+
 int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
-                      int max_blocks, void* stream) {
+                      int max_blocks, int block_threads, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (!rc) rc = check_peers(w, ws, peer_ws);
@@ -769,8 +775,9 @@ int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const*
     set_error("bad peer range first=%d count=%d (world %d)", first, count, w.pb.world);
     return SCLIP_ERR_ARGUMENT;
   }
+  if (bad_block(block_threads, 1024)) return SCLIP_ERR_ARGUMENT;
   if (count == 0) return SCLIP_OK;
-  return launch_pull_shards(w, peer_ws, first, count, max_blocks, static_cast<cudaStream_t>(stream));
+  return launch_pull_shards(w, peer_ws, first, count, max_blocks, block_threads, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_pull_col_lse(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* col_lse_all,
@@ -800,7 +807,7 @@ int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* p
 }
 
 int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* const* peer_ws, int max_blocks,
-                           void* stream) {
+                           int block_threads, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (!rc) rc = check_peers(w, ws, peer_ws);
@@ -809,7 +816,8 @@ int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* c
     set_error("dim must be a multiple of 4");
     return SCLIP_ERR_ARGUMENT;
   }
-  return launch_pull_reduce(w, peer_ws, max_blocks, static_cast<cudaStream_t>(stream));
+  if (bad_block(block_threads, 512)) return SCLIP_ERR_ARGUMENT;
+  return launch_pull_reduce(w, peer_ws, max_blocks, block_threads, static_cast<cudaStream_t>(stream));
 }
 
 // the single-GPU convenience calls remember, per workspace, whether the last forward stashed

@@ -757,7 +757,7 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
 namespace sclip {
 
 int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
-                       cudaStream_t stream) {
+                       int block_threads, cudaStream_t stream) {
   PullShardArgs a;
   memset(&a, 0, sizeof(a));
   const int world = w.pb.world, rank = w.pb.row_offset / w.pb.rows_local;
@@ -776,12 +776,13 @@ int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first
   a.dim = w.pb.dim;
   int bx = max_blocks / count;
   if (bx < 1) bx = 1;
-  pull_shards_kernel<<<dim3(bx, count), 1024, 0, stream>>>(a);
+  pull_shards_kernel<<<dim3(bx, count), block_threads, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
-int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, cudaStream_t stream) {
+int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, int block_threads,
+                       cudaStream_t stream) {
   PullReduceArgs a;
   memset(&a, 0, sizeof(a));
   for (int r = 0; r < w.pb.world; ++r) a.peer[r] = static_cast<const uint8_t*>(peer_ws[r]);
@@ -794,10 +795,10 @@ int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_b
   a.dim = w.pb.dim;
   const int blocks = max_blocks < 1 ? 1 : max_blocks;
   switch (w.pb.world) {
-    case 2: pull_reduce_kernel<2><<<blocks, 512, 0, stream>>>(a); break;
-    case 4: pull_reduce_kernel<4><<<blocks, 512, 0, stream>>>(a); break;
-    case 8: pull_reduce_kernel<8><<<blocks, 512, 0, stream>>>(a); break;
-    default: pull_reduce_kernel<0><<<blocks, 512, 0, stream>>>(a); break;
+    case 2: pull_reduce_kernel<2><<<blocks, block_threads, 0, stream>>>(a); break;
+    case 4: pull_reduce_kernel<4><<<blocks, block_threads, 0, stream>>>(a); break;
+    case 8: pull_reduce_kernel<8><<<blocks, block_threads, 0, stream>>>(a); break;
+    default: pull_reduce_kernel<0><<<blocks, block_threads, 0, stream>>>(a); break;
   }
   SCLIP_LAUNCHED();
   return SCLIP_OK;

@@ -83,9 +83,9 @@ def test_peer_memory_and_scorer_calls_validate_their_arguments():
     fake_ws = ctypes.c_void_p(1 << 20)                                                         # 256-byte aligned, never touched
     single = _lib.Problem(128, 128, 0, 512, 1, 0, 1, 0)
     table = (ctypes.c_void_p * 2)(1 << 20, 2 << 20)
-    assert lib.sclip_pull_shards(ctypes.byref(single), fake_ws, table, 1, 1, 8, None) == -1    # world must be >= 2
+    assert lib.sclip_pull_shards(ctypes.byref(single), fake_ws, table, 1, 1, 8, 256, None) == -1    # world must be >= 2
     sharded = _lib.Problem(128, 256, 128, 512, 1, 0, 2, 0)                                     # rank 1 of 2
-    assert lib.sclip_pull_shards(ctypes.byref(sharded), fake_ws, table, 1, 1, 8, None) == -1   # peer_ws[rank] != ws
+    assert lib.sclip_pull_shards(ctypes.byref(sharded), fake_ws, table, 1, 1, 8, 256, None) == -1   # peer_ws[rank] != ws
     assert b"own workspace" in lib.sclip_last_error()
-    assert lib.sclip_pull_reduce_cols(ctypes.byref(sharded), fake_ws, None, 8, None) == -1
+    assert lib.sclip_pull_reduce_cols(ctypes.byref(sharded), fake_ws, None, 8, 256, None) == -1
     assert lib.sclip_kernel_launches() == 0                                                    # nothing was launched

@@ -62,20 +62,15 @@ class TriContrastiveConfig:
         if stash not in ("auto", True, False):
             raise ValueError(f"stash={stash!r}")
         self.stash = stash
-        # stash mode: apply the stash -> G' factors in a separate in-place HBM pass (False, default) or to the A tiles
-        # in shared memory inside the gradient GEMMs (True).  Measured on B200 (B = 32768, D = 768): the separate pass
-        # costs 2.4 ms, the in-GEMM conversion makes the GEMMs 3.4 ms slower -- the tile mainloop is already bound by
-        # shared-memory bandwidth (TMA writes + tensor-core reads ~ 125 B/clk/SM), which the conversion's extra
-        # read + write of every A tile exceeds.
+        # (round 1 also tried converting the stash inside the gradient GEMMs, `fuse_scale`: 3.4 ms more GEMM time for a
+        # 2.4 ms pass saved, and no place for the fp32 identity term of `sclip_backward_scale`; the code is at commit 5c56fe2)
         if fuse_scale:
-            raise ValueError("fuse_scale was a round-1 experiment (stash converted inside the gradient GEMMs): slower than "
-                             "the HBM pass and without the fp32 identity term of sclip_backward_scale; removed")
-        self.fuse_scale = False
+            raise ValueError("fuse_scale was a round-1 experiment and has been removed (see DESIGN.md section 9)")
         # world_size > 1: how the shards move between ranks.
         #   "p2p"  -- the workspace lives in symmetric memory (torch.distributed._symmetric_memory: every rank's blob
         #             mapped into every process over NVLink / NVSwitch) and the exchanges are kernels of the library
-        #             that load straight from the peers' workspaces (pull all-gather of the operand shards in two waves
-        #             under the tiles, pull reduce of the column-role gradients under the row-role GEMMs);
+        #             that load straight from the peers' workspaces (pull all-gather of the operand shards in waves
+        #             of 1, 2, 4 ranks under the tiles, pull reduce of the column-role gradients under the row-role GEMMs);
         #   "nccl" -- torch.distributed collectives (all-gather / reduce-scatter) on a side stream;
         #   "auto" -- "p2p" on CUDA when symmetric memory is available, else "nccl".
         if transport not in ("auto", "p2p", "nccl"):

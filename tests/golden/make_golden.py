@@ -40,6 +40,10 @@ CASES = [
     ("b2048x512_planted", 2048, 512, 18, False, (2.6592, 3.2, 3.9), (1.0, 1.0, 1.0), 0.3),
     ("b4096x768_bf16", 4096, 768, 19, True, (2.6592, 2.6592, 2.6592), (1.0, 1.0, 1.0), 0.0),
     ("b1000x1024_bf16_ln100", 1000, 1024, 20, True, (LN100, LN100, LN100), (1.0, 0.5, 0.25), 0.08),
+    # trained-like batch, sharply peaked softmax (the positive-pair entry of G' is a small difference): stash path
+    ("b300x768_bf16_peaked", 300, 768, 21, True, (math.log(43.5),) * 3, (0.5, 1.0, 0.25), 0.25),
+    # one pair per forward kernel: s = 14.3 and s = 43.5 take the folded-exponent epilogue, s = 100 the per-tile maximum
+    ("b300x768_bf16_mixed", 300, 768, 22, True, (2.6592, math.log(43.5), LN100), (0.5, 1.0, 0.25), 0.12),
 ]
 
 FULL_GRAD_MAX_B = 64
@@ -69,12 +73,20 @@ def summarise(name, res, b, d, seed):
     return out
 
 
-def main():
+def main(only=None):
+    """only: comma-separated case names to (re)generate; the other fixtures and their manifest entries are kept."""
     import torch
 
     torch.set_num_threads(os.cpu_count() or 1)
     manifest = []
+    keep = set()
+    if only:
+        keep = set(only.split(","))
+        with open(os.path.join(HERE, "manifest.json")) as f:
+            manifest = [c for c in json.load(f)["cases"] if c["name"] not in keep]
     for name, b, d, seed, bf16, t3, g3, planted in CASES:
+        if only and name not in keep:
+            continue
         embs = case_inputs(b, d, seed, bf16, planted)
         ref64 = ref_import.reference_tail(*embs, t3, g3, dtype=torch.float64)
         ref32 = ref_import.reference_tail(*embs, t3, g3, dtype=torch.float32)
@@ -87,10 +99,12 @@ def main():
              "planted": planted, "loss_fp64": [float(x) for x in ref64["loss"]]}
         )
         print(name, ref64["loss"], ref64["dscale"], flush=True)
+    order = {c[0]: i for i, c in enumerate(CASES)}
+    manifest.sort(key=lambda c: order.get(c["name"], 1 << 30))
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump({"generator": "tests/golden/make_golden.py", "reference": "model.py:52-58,247-272 (unmodified, imported)",
                    "cases": manifest}, f, indent=1)
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

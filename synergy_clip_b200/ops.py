@@ -484,6 +484,30 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
     return loss3
 
 
+def _pull_waves(world: int, pipelined: bool):
+    """How many ranks each pull wave brings in: 1, 2, 4, ... (the first wave lands under the tiles of this rank's own
+    columns, each following one under the tiles of the wave before it); one wave of everything when not pipelined."""
+    waves, left = [], world - 1
+    while left > 0:
+        n = min(left, 1 << len(waves)) if pipelined else left
+        waves.append(n)
+        left -= n
+    return waves
+
+
+def _wave_column_ranges(world: int, rank: int, tiles_per_rank: int, waves):
+    """(first column tile, tile count) of this rank's own columns and of every wave, in launch order.  Wave i holds the
+    columns of ranks rank + 1 + (ranks of earlier waves) ..., modulo world: a range may wrap around the last column
+    tile (the tile kernels take it modulo the tile count, SCLIP_FWD_WRAP)."""
+    col_tiles = world * tiles_per_rank
+    out = [(rank * tiles_per_rank, tiles_per_rank)]
+    begin = ((rank + 1) % world) * tiles_per_rank
+    for n in waves:
+        out.append((begin, n * tiles_per_rank))
+        begin = (begin + n * tiles_per_rank) % col_tiles
+    return out
+
+
 def _forward_p2p(ws: "_SymmWorkspace", t3, cfg: TriContrastiveConfig, stash: bool, loss3: torch.Tensor):
     """world > 1, workspace in symmetric memory.  After the prologue the operand shards of the other ranks are pulled
     over NVLink by `sclip_pull_shards` in two waves on the side stream while the tiles of the columns already present
@@ -506,13 +530,7 @@ def _forward_p2p(ws: "_SymmWorkspace", t3, cfg: TriContrastiveConfig, stash: boo
     pull_threads = 256 if coresident else 1024
     ready = torch.cuda.Event()
     ready.record(cur)
-    # waves of 1, 2, 4, ... ranks: the first lands under the tiles of this rank's own columns, each following one
-    # under the tiles of the wave before it
-    waves, left = [], world - 1
-    while left > 0:
-        n = min(left, 1 << len(waves)) if pipelined else left
-        waves.append(n)
-        left -= n
+    waves = _pull_waves(world, pipelined)
     trace = _TRACE is not None
     landed = [torch.cuda.Event(enable_timing=trace) for _ in waves]
     after_barrier = torch.cuda.Event(enable_timing=True) if trace else None
@@ -533,19 +551,17 @@ def _forward_p2p(ws: "_SymmWorkspace", t3, cfg: TriContrastiveConfig, stash: boo
             _LAST_COMM_EVENTS = [("fwd_barrier", after_barrier)] + [(f"pull{i + 1}", ev) for i, ev in enumerate(landed)]
 
     if pipelined:
-        lo = off // 256
+        ranges = _wave_column_ranges(world, off // bl, tiles_per_rank, waves)
         prev = be.set_max_sms(_sm_count(dev) - cfg.comm_sms)  # the pull kernels run on the SMs left free
         try:
-            be.forward_tiles_cols(ws, t3, 7, lo, lo + tiles_per_rank, stash)
+            be.forward_tiles_cols(ws, t3, 7, ranges[0][0], ranges[0][0] + ranges[0][1], stash)
             start_pulls()
             _mark("forward_tiles_local")
-            begin = (lo + tiles_per_rank) % lay.col_tiles
-            for i, (n, ev) in enumerate(zip(waves, landed)):
+            for i, ((begin, count), ev) in enumerate(zip(ranges[1:], landed)):
                 cur.wait_event(ev)
                 if i == len(waves) - 1:
                     be.set_max_sms(prev)  # nothing left to pull: the last (largest) wave's tiles take every SM
-                be.forward_tiles_cols(ws, t3, 7, begin, begin + n * tiles_per_rank, stash, wrap=True)
-                begin = (begin + n * tiles_per_rank) % lay.col_tiles
+                be.forward_tiles_cols(ws, t3, 7, begin, begin + count, stash, wrap=True)
                 if i < len(waves) - 1:
                     _mark(f"forward_tiles_wave{i + 1}")
         finally:

@@ -175,3 +175,35 @@ def test_ddp_wrapper_averages_to_the_global_batch_gradient(tmp_path):
         want, got = p.grad, grads[0][k].double()
         err = (got - want).norm() / want.norm()
         assert err < 1e-5, (k, float(err))
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 5, 6, 7, 8, 16])
+def test_pull_waves_cover_every_column_tile_exactly_once(world):
+    """Host logic of the peer-memory forward: the pull waves bring in every other rank exactly once, in the order
+    rank + 1, rank + 2, ... (the order `sclip_pull_shards` copies them), and the column-tile ranges handed to the tile
+    kernel -- own columns first, then wave by wave, wrapping around the last tile -- partition the column tiles."""
+    from synergy_clip_b200 import ops
+
+    tiles_per_rank = 3
+    col_tiles = world * tiles_per_rank
+    for pipelined in (True, False):
+        waves = ops._pull_waves(world, pipelined)
+        assert sum(waves) == world - 1 and all(n >= 1 for n in waves)
+        if pipelined:
+            assert waves[0] == 1 and all(b <= 2 * a for a, b in zip(waves, waves[1:]))
+        else:
+            assert len(waves) == 1
+        for rank in range(world):
+            ranges = ops._wave_column_ranges(world, rank, tiles_per_rank, waves)
+            seen = []
+            for begin, count in ranges:
+                assert 0 <= begin < col_tiles and 0 < count <= col_tiles
+                seen += [(begin + k) % col_tiles for k in range(count)]
+            assert sorted(seen) == list(range(col_tiles))
+            assert seen[:tiles_per_rank] == [rank * tiles_per_rank + k for k in range(tiles_per_rank)]
+            # wave i's columns belong to the ranks its pull copied: rank + 1 + (ranks of the earlier waves) ...
+            first = 1
+            for (begin, count), n in zip(ranges[1:], waves):
+                owners = sorted({((begin + k) % col_tiles) // tiles_per_rank for k in range(count)})
+                assert owners == sorted((rank + first + i) % world for i in range(n))
+                first += n

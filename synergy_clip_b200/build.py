@@ -54,26 +54,57 @@ def _compile(nvcc: str, src: str, obj: str) -> str:
     return res.stderr
 
 
+def _up_to_date(stamp: str, digest: str) -> bool:
+    try:
+        with open(stamp) as f:
+            return os.path.exists(LIB) and f.read().strip() == digest
+    except OSError:
+        return False
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Incremental build.  Safe when several ranks (mp.spawn / torchrun) import the package at once on a fresh checkout:
+    one process holds an exclusive file lock while it compiles into a private temporary directory, the library and its
+    digest stamp appear by atomic rename, and the others re-check the stamp once they get the lock."""
+    import fcntl
+    import tempfile
+
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "libsclip.digest")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+    if not force and _up_to_date(stamp, digest):
         return LIB
-    nvcc = _nvcc()
-    objs = [os.path.join(LIBDIR, s.replace(".cu", ".o")) for s in SOURCES]
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
-        logs = list(pool.map(lambda so: _compile(nvcc, *so), zip(SOURCES, objs)))
-    with open(os.path.join(LIBDIR, "ptxas.log"), "w") as f:
-        f.write("\n".join(logs))
-    if verbose:
-        print("\n".join(logs))
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
-    res = subprocess.run(link, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
-    with open(stamp, "w") as f:
-        f.write(digest)
+    with open(os.path.join(LIBDIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp, digest):  # another process built it while this one waited
+                return LIB
+            nvcc = _nvcc()
+            with tempfile.TemporaryDirectory(dir=LIBDIR, prefix=".build-") as tmp:
+                objs = [os.path.join(tmp, s.replace(".cu", ".o")) for s in SOURCES]
+                with concurrent.futures.ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+                    logs = list(pool.map(lambda so: _compile(nvcc, *so), zip(SOURCES, objs)))
+                if verbose:
+                    print("\n".join(logs))
+                tmp_lib = os.path.join(tmp, "libsclip.so")
+                link = [nvcc, "-shared", "-o", tmp_lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-Xcompiler", "-fPIC"]
+                res = subprocess.run(link, capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+                tmp_log = os.path.join(tmp, "ptxas.log")
+                with open(tmp_log, "w") as f:
+                    f.write("\n".join(logs))
+                tmp_stamp = os.path.join(tmp, "libsclip.digest")
+                with open(tmp_stamp, "w") as f:
+                    f.write(digest)
+                if os.path.exists(stamp):
+                    os.remove(stamp)  # never a new library under an old stamp or the reverse
+                os.replace(tmp_log, os.path.join(LIBDIR, "ptxas.log"))
+                os.replace(tmp_lib, LIB)
+                os.replace(tmp_stamp, stamp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

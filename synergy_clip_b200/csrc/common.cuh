@@ -42,7 +42,6 @@ struct Segment {
   int a_mn;    // 0: operand stored [rows][k] (K-major)   1: stored [k][rows] (MN-major)
   int b_mn;
   int num_kb;  // number of BK-wide k blocks
-  int map_a64;  // K-major A operand with a 64-row box (multicast halves of the wide GEMM tiles); -1 if unused
 };
 
 struct Job {
@@ -129,8 +128,6 @@ struct FwdParams {
   const float* diag_all;     // [3][rows_global] positive-pair logits (stash scaling)
   int stages;       // depth of the TMA ring
   int pair_filter;  // forward_tiles_kernel: skip the pairs forward_fast_kernel has taken (s < 44)
-  int debug;        // profiling experiments only (SCLIP_DEBUG): 1 = epilogue releases the accumulator untouched,
-                    // 2 = epilogue only loads the accumulator from TMEM
   float acc_scale;  // accumulator -> cosine (1 in F16 mode, 2^-16 in F16X3 mode)
 };
 

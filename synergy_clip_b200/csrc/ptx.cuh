@@ -272,6 +272,50 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int fmt, int
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+
+// ---------------------------------------------------------------- warp-uniform role helpers
+// The single-thread pipeline roles (TMA producer, MMA issuer) are written as CONVERGENT warp code: all 32 lanes run the
+// loops and the waits, every operand is computed from warp-uniform values, and only the issuing instruction sits under
+// `if (elected)`.  nvcc then keeps the operands on the uniform datapath and emits the UTMALDG / UTCHMMA back to back;
+// the same loops under `if (lane == 0)` compile to an ELECT / R2UR.BROADCAST / branch sequence per instruction
+// (about 180 SASS instructions per k block, which made the issuing thread -- not the tensor pipe or L2 -- the bound
+// of the similarity tiles in round 1: profiles/r2_summary.md).  These variants take shared-memory addresses as u32.
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_u32(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                    int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_1sm_u32(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_u32(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+// Shared-memory matrix descriptor split into its two words: the high word (stride byte offset, version, swizzle) is a
+// constant of the operand layout, the low word is (address >> 4) | (leading byte offset >> 4) << 16, so stepping through
+// a stage or along k is one 32-bit add.
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 }  // namespace ptx
 }  // namespace sclip
 

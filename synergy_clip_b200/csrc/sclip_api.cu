@@ -335,9 +335,7 @@ struct MapTable {
   }
 };
 
-Segment seg(int a, int b, int a_mn, int b_mn, int num_kb, int a64 = -1) {
-  return Segment{a, b, a_mn, b_mn, num_kb, a64};
-}
+Segment seg(int a, int b, int a_mn, int b_mn, int num_kb) { return Segment{a, b, a_mn, b_mn, num_kb}; }
 
 // similarity job of pair p (forward and the backward recompute)
 void similarity_job(const Workspace& w, MapTable& t, int p, Job* job) {
@@ -463,10 +461,6 @@ int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float
     if (tab.rc) return tab.rc;
   }
   p.stages = ring_stages(p.stash ? 4 : 0);
-  {
-    const char* e = getenv("SCLIP_DEBUG");
-    p.debug = e != nullptr ? atoi(e) : 0;
-  }
   p.acc_scale = w.pb.math == SCLIP_MATH_F16X3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
   return launch_forward_tiles(p, cta_group(), epi_warps(), static_cast<cudaStream_t>(stream));
 }
@@ -566,8 +560,7 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
         job.seg[job.nseg++] = seg(tab.use(kGloK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
         job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
       }
-      // (the 64 x 64 box map of the MN-major view doubles as the 64-row K-major box of the multicast halves)
-      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g, tab.use(kGMN + pr));
+      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
     } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
       const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
       if (x3) {
@@ -870,9 +863,7 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
     rc = b_mn ? make_map(&p.maps[1], b, n, k, ldb, 64, BK) : make_map(&p.maps[1], b, k, n, ldb, BK, BN / cta_group());
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK), 2};
-  if (!a_mn) rc = make_map(&p.maps[2], a, k, m, lda, BK, 64);  // 64-row boxes (multicast halves of the wide tiles)
-  if (rc) return rc;
+  p.jobs[0].seg[0] = Segment{0, 1, a_mn ? 1 : 0, b_mn ? 1 : 0, ceil_div(k, BK)};
   p.jobs[0].nseg = 1;
   p.jobs[0].ksplits = 1;
   p.jobs[0].m_tiles = ceil_div(m, BM * cta_group());

@@ -80,97 +80,142 @@ __device__ __forceinline__ void split_range(int num_kb, int split, int ksplits, 
 }
 
 // ---------------------------------------------------------------------------------------------- mainloop roles
-template <int CG>
-__device__ __forceinline__ void producer_tile(const CUtensorMap* maps, const Job& job, const Tile& t, uint32_t rank,
-                                              uint8_t* smem, PipeBarriers* bars, int stages, RingState& rs) {
+// Both roles are convergent warp code (see ptx.cuh, "warp-uniform role helpers"): every lane runs the loops and the
+// barrier waits, `elected` is true in exactly one lane, and only the TMA / MMA / commit instructions sit under it.
+template <int CG, bool A_MN, bool B_MN>
+__device__ __forceinline__ void produce_kblocks(const CUtensorMap* ma, const CUtensorMap* mb, int m0, int n0, int kb_lo,
+                                                int kb_hi, uint32_t smem0, uint32_t full_sig0, uint32_t full_loc0,
+                                                PipeBarriers* bars, int stages, RingState& rs, bool elected, bool arm) {
   using G = Geo<CG>;
-  const int m0 = t.m0 + static_cast<int>(rank) * BM;         // this CTA's accumulator rows
-  const int n0 = t.n0 + static_cast<int>(rank) * G::kBRows;  // this CTA's share of the B rows
-  for (int s = 0; s < job.nseg; ++s) {
-    const Segment seg = job.seg[s];
-    const CUtensorMap* ma = maps + seg.map_a;
-    const CUtensorMap* mb = maps + seg.map_b;
-    int kb_lo, kb_hi;
-    split_range(seg.num_kb, t.split, job.ksplits, kb_lo, kb_hi);
-    for (int kb = kb_lo; kb < kb_hi; ++kb) {
-      mbar_wait_bounded<false>(&bars->empty[rs.stage], rs.phase ^ 1u, 1);
-      uint8_t* sa = smem + rs.stage * G::kStageBytes;
-      uint8_t* sb = sa + A_STAGE_BYTES;
+  for (int kb = kb_lo; kb < kb_hi; ++kb) {
+    mbar_wait_bounded<false>(&bars->empty[rs.stage], rs.phase ^ 1u, 1);
+    if (elected) {
+      const uint32_t sa = smem0 + rs.stage * G::kStageBytes;
+      const uint32_t sb = sa + A_STAGE_BYTES;
+      const uint32_t bar = full_sig0 + rs.stage * 8;
       const int k = kb * BK;
+      // CG 2: both CTAs of the pair signal the leader's barrier; the leader arms it for the bytes of both
+      if (arm) mbar_expect_tx_u32(full_loc0 + rs.stage * 8, CG * G::kLoadBytes);
       if constexpr (CG == 1) {
-        uint64_t* bar = &bars->full[rs.stage];
-        mbar_expect_tx(bar, G::kLoadBytes);
-        if (!seg.a_mn) {
-          tma_load_2d(sa, ma, bar, k, m0);
+        if constexpr (!A_MN) {
+          tma_load_2d_u32(sa, ma, bar, k, m0);
         } else {
 #pragma unroll
-          for (int g = 0; g < BM / 64; ++g) tma_load_2d(sa + g * MN_BOX_BYTES, ma, bar, m0 + g * 64, k);
+          for (int g = 0; g < BM / 64; ++g) tma_load_2d_u32(sa + g * MN_BOX_BYTES, ma, bar, m0 + g * 64, k);
         }
-        if (!seg.b_mn) {
-          tma_load_2d(sb, mb, bar, k, n0);
+        if constexpr (!B_MN) {
+          tma_load_2d_u32(sb, mb, bar, k, n0);
         } else {
 #pragma unroll
-          for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
+          for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d_u32(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
         }
       } else {
-        // both CTAs of the pair signal the leader's barrier; the leader arms it for the bytes of both
-        const uint32_t bar = mapa(smem_u32(&bars->full[rs.stage]), 0);
-        if (rank == 0) mbar_expect_tx(&bars->full[rs.stage], CG * G::kLoadBytes);
-        if (!seg.a_mn) {
-          tma_load_2d_2sm(sa, ma, bar, k, m0);
+        if constexpr (!A_MN) {
+          tma_load_2d_2sm_u32(sa, ma, bar, k, m0);
         } else {
 #pragma unroll
-          for (int g = 0; g < BM / 64; ++g) tma_load_2d_2sm(sa + g * MN_BOX_BYTES, ma, bar, m0 + g * 64, k);
+          for (int g = 0; g < BM / 64; ++g) tma_load_2d_2sm_u32(sa + g * MN_BOX_BYTES, ma, bar, m0 + g * 64, k);
         }
-        if (!seg.b_mn) {
-          tma_load_2d_2sm(sb, mb, bar, k, n0);
+        if constexpr (!B_MN) {
+          tma_load_2d_2sm_u32(sb, mb, bar, k, n0);
         } else {
 #pragma unroll
-          for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d_2sm(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
+          for (int g = 0; g < G::kBRows / 64; ++g) tma_load_2d_2sm_u32(sb + g * MN_BOX_BYTES, mb, bar, n0 + g * 64, k);
         }
       }
-      rs.advance(stages);
     }
+    rs.advance(stages);
   }
 }
 
+// Called by all lanes of the producer warp.
 template <int CG>
-__device__ __forceinline__ void mma_tile(const Job& job, const Tile& t, uint8_t* smem, PipeBarriers* bars, int stages,
-                                         RingState& rs, uint32_t tmem_acc, int acc, uint32_t acc_phase) {
+__device__ __forceinline__ void producer_tile(const CUtensorMap* maps, const Job& job, const Tile& t, uint32_t rank,
+                                              uint8_t* smem, PipeBarriers* bars, int stages, RingState& rs,
+                                              bool elected) {
   using G = Geo<CG>;
-  // the epilogue must have drained this accumulator (two tiles ago)
-  mbar_wait_bounded<false>(&bars->tmem_empty[acc], acc_phase ^ 1u, 4);
-  tc_fence_after();
-  uint32_t accumulate = 0;
+  const int m0 = t.m0 + static_cast<int>(rank) * BM;         // this CTA's accumulator rows
+  const int n0 = t.n0 + static_cast<int>(rank) * G::kBRows;  // this CTA's share of the B rows
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t full_loc0 = smem_u32(&bars->full[0]);
+  const uint32_t full_sig0 = CG == 1 ? full_loc0 : mapa(full_loc0, 0);
+  const bool arm = rank == 0;
   for (int s = 0; s < job.nseg; ++s) {
-    const Segment seg = job.seg[s];
-    const uint32_t idesc = make_idesc_f16(BM * CG, BN, /*fp16*/ 0, seg.a_mn, seg.b_mn);
+    const CUtensorMap* ma = maps + job.seg[s].map_a;
+    const CUtensorMap* mb = maps + job.seg[s].map_b;
+    const int a_mn = job.seg[s].a_mn, b_mn = job.seg[s].b_mn;
     int kb_lo, kb_hi;
-    split_range(seg.num_kb, t.split, job.ksplits, kb_lo, kb_hi);
-    for (int kb = kb_lo; kb < kb_hi; ++kb) {
-      mbar_wait_bounded<false>(&bars->full[rs.stage], rs.phase, 2);
-      tc_fence_after();
-      const uint32_t a_base = smem_u32(smem + rs.stage * G::kStageBytes);
-      const uint32_t b_base = a_base + A_STAGE_BYTES;
+    split_range(job.seg[s].num_kb, t.split, job.ksplits, kb_lo, kb_hi);
+    if (!a_mn && !b_mn)
+      produce_kblocks<CG, false, false>(ma, mb, m0, n0, kb_lo, kb_hi, smem0, full_sig0, full_loc0, bars, stages, rs, elected, arm);
+    else if (!a_mn)
+      produce_kblocks<CG, false, true>(ma, mb, m0, n0, kb_lo, kb_hi, smem0, full_sig0, full_loc0, bars, stages, rs, elected, arm);
+    else if (!b_mn)
+      produce_kblocks<CG, true, false>(ma, mb, m0, n0, kb_lo, kb_hi, smem0, full_sig0, full_loc0, bars, stages, rs, elected, arm);
+    else
+      produce_kblocks<CG, true, true>(ma, mb, m0, n0, kb_lo, kb_hi, smem0, full_sig0, full_loc0, bars, stages, rs, elected, arm);
+  }
+}
+
+// descriptor steps: K-major operand: 8-row groups 1024 B apart, k step of 16 elements = 32 B inside the 128-byte swizzle
+// row (low word + 2).  MN-major operand: 64-element groups one box (8 KiB) apart, 8-k groups 1024 B apart, k step =
+// 16 rows of 128 B = 2 KiB (low word + 128).
+template <bool MN>
+struct OperandDesc {
+  static constexpr uint32_t kLbo = MN ? MN_BOX_BYTES : 16;
+  static constexpr uint32_t kStep = MN ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+};
+
+template <int CG, bool A_MN, bool B_MN>
+__device__ __forceinline__ void mma_kblocks(int nkb, uint32_t smem0, uint32_t empty0, PipeBarriers* bars, int stages,
+                                            RingState& rs, uint32_t tmem_acc, uint32_t& accumulate, bool elected) {
+  using G = Geo<CG>;
+  constexpr uint32_t idesc = make_idesc_f16(BM * CG, BN, /*fp16*/ 0, A_MN, B_MN);
+  constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+  for (int kb = 0; kb < nkb; ++kb) {
+    mbar_wait_bounded<false>(&bars->full[rs.stage], rs.phase, 2);
+    tc_fence_after();
+    if (elected) {
+      const uint32_t a_lo = smem_desc_lo(smem0 + rs.stage * G::kStageBytes, OperandDesc<A_MN>::kLbo);
+      const uint32_t b_lo = smem_desc_lo(smem0 + rs.stage * G::kStageBytes + A_STAGE_BYTES, OperandDesc<B_MN>::kLbo);
 #pragma unroll
       for (int k = 0; k < BK / UMMA_K; ++k) {
-        // K-major: 8-row groups 1024 B apart, k step = 32 B inside the 128-byte swizzle row.
-        // MN-major: 64-element groups one box (8 KiB) apart, 8-k groups 1024 B apart, k step = 16 rows = 2 KiB.
-        const uint64_t adesc = seg.a_mn ? make_smem_desc_sw128(a_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
-                                        : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
-        const uint64_t bdesc = seg.b_mn ? make_smem_desc_sw128(b_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
-                                        : make_smem_desc_sw128(b_base + k * (UMMA_K * 2), 16, 1024);
-        umma_f16<CG>(tmem_acc, adesc, bdesc, idesc, accumulate);
+        umma_f16<CG>(tmem_acc, smem_desc_join(a_lo + k * OperandDesc<A_MN>::kStep, hi),
+                     smem_desc_join(b_lo + k * OperandDesc<B_MN>::kStep, hi), idesc, accumulate);
         accumulate = 1;
       }
       // frees the smem slot (in both CTAs) once these MMAs have read it
-      if constexpr (CG == 1) umma_commit_1sm(&bars->empty[rs.stage]);
-      else umma_commit_2sm(&bars->empty[rs.stage], 0b11);
-      rs.advance(stages);
+      if constexpr (CG == 1) umma_commit_1sm_u32(empty0 + rs.stage * 8);
+      else umma_commit_2sm_u32(empty0 + rs.stage * 8, 0b11);
     }
+    rs.advance(stages);
   }
-  if constexpr (CG == 1) umma_commit_1sm(&bars->tmem_full[acc]);
-  else umma_commit_2sm(&bars->tmem_full[acc], 0b11);
+}
+
+// Called by all lanes of the MMA warp of the leader CTA.
+template <int CG>
+__device__ __forceinline__ void mma_tile(const Job& job, const Tile& t, uint8_t* smem, PipeBarriers* bars, int stages,
+                                         RingState& rs, uint32_t tmem_acc, int acc, uint32_t acc_phase, bool elected) {
+  // the epilogue must have drained this accumulator (two tiles ago)
+  mbar_wait_bounded<false>(&bars->tmem_empty[acc], acc_phase ^ 1u, 4);
+  tc_fence_after();
+  const uint32_t smem0 = smem_u32(smem);
+  const uint32_t empty0 = smem_u32(&bars->empty[0]);
+  uint32_t accumulate = 0;
+  for (int s = 0; s < job.nseg; ++s) {
+    const int a_mn = job.seg[s].a_mn, b_mn = job.seg[s].b_mn;
+    int kb_lo, kb_hi;
+    split_range(job.seg[s].num_kb, t.split, job.ksplits, kb_lo, kb_hi);
+    const int nkb = kb_hi - kb_lo;
+    if (!a_mn && !b_mn) mma_kblocks<CG, false, false>(nkb, smem0, empty0, bars, stages, rs, tmem_acc, accumulate, elected);
+    else if (!a_mn) mma_kblocks<CG, false, true>(nkb, smem0, empty0, bars, stages, rs, tmem_acc, accumulate, elected);
+    else if (!b_mn) mma_kblocks<CG, true, false>(nkb, smem0, empty0, bars, stages, rs, tmem_acc, accumulate, elected);
+    else mma_kblocks<CG, true, true>(nkb, smem0, empty0, bars, stages, rs, tmem_acc, accumulate, elected);
+  }
+  if (elected) {
+    if constexpr (CG == 1) umma_commit_1sm_u32(smem_u32(&bars->tmem_full[acc]));
+    else umma_commit_2sm_u32(smem_u32(&bars->tmem_full[acc]), 0b11);
+  }
 }
 
 // Common prologue: barrier init, TMEM allocation (all 512 columns = two accumulators).
@@ -385,27 +430,25 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == EW) {
-    if (lane == 0) {
-      RingState rs;
-      for (int t = cluster_id; t < total; t += num_clusters) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
-        tile.job = pairs[tile.job];
-        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
-      }
+    const bool elected = elect_one();
+    RingState rs;
+    for (int t = cluster_id; t < total; t += num_clusters) {
+      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
+      tile.job = pairs[tile.job];
+      producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs, elected);
     }
-    __syncwarp();
   } else if (warp == EW + 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the leader CTA issues the MMAs of the pair
+      const bool elected = elect_one();
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
         Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
         tile.job = pairs[tile.job];
         const int acc = it & 1;
-        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1, elected);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;              // TMEM lane quarter this warp may read
     const int slice = warp >> 2;   // which CS accumulator columns
@@ -469,21 +512,6 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
 
       mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
       tc_fence_after();
-      if (P.debug != 0) {  // profiling experiments: how long does the mainloop take without the epilogue?
-        if (P.debug == 2) {
-          uint32_t v[32];
-          uint32_t sink = 0;
-          for (int ch = 0; ch < NCH; ++ch) {
-            tmem_ld_block32(taddr + ch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sink ^= v[i];
-          }
-          if (sink == 0x12345678u) P.tile_ref[0] = 1.f;
-        }
-        release_accumulator<CG>(&bars, acc, rank, lane);
-        continue;
-      }
 
       // exponent reference of this tile, in log2 units.  s < 64: |logit| <= s (cosines), so exp(logit) and its sums
       // are normal fp32 numbers without any shift; otherwise the true maximum of the tile is taken in a first pass.
@@ -704,27 +732,25 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == EW) {
-    if (lane == 0) {
-      RingState rs;
-      for (int t = cluster_id; t < total; t += num_clusters) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
-        tile.job = pairs[tile.job];
-        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
-      }
+    const bool elected = elect_one();
+    RingState rs;
+    for (int t = cluster_id; t < total; t += num_clusters) {
+      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
+      tile.job = pairs[tile.job];
+      producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs, elected);
     }
-    __syncwarp();
   } else if (warp == EW + 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the leader CTA issues the MMAs of the pair
+      const bool elected = elect_one();
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
         Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
         tile.job = pairs[tile.job];
         const int acc = it & 1;
-        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1, elected);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;        // TMEM lane quarter
     const int slice = warp >> 2;   // column half of the tile
@@ -793,24 +819,6 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
 
       mbar_wait_bounded<false>(&bars.tmem_full[acc], (it >> 1) & 1, 3);
       tc_fence_after();
-      const bool dbg_nostore = (P.debug & 16) != 0, dbg_nostage = (P.debug & 32) != 0, dbg_nostat = (P.debug & 64) != 0;
-      if ((P.debug & 15) != 0) {  // profiling experiments: 1 = mainloop without the epilogue, 2 / 3 = only the TMEM loads
-        if ((P.debug & 15) >= 2) {  //                     (2: 16x256b fragments, 3: 32x32b rows)
-          uint32_t v[32];
-          uint32_t sink = 0;
-          for (int ch = 0; ch < NCH; ++ch) {
-            if ((P.debug & 15) == 2) tmem_ld_block32(taddr + ch * 32, v);
-            else tmem_ld_32x32b_x32(taddr + ch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) sink ^= v[i];
-          }
-          if (sink == 0x12345678u) P.tile_ref[0] = 1.f;
-        }
-        release_accumulator<CG>(&bars, acc, rank, lane);
-        continue;
-      }
-
       uint64_t rp2[4] = {0ull, 0ull, 0ull, 0ull};  // row partials (pairs of adjacent columns), in e' units
       uint32_t va[32], vb[32];
       auto process = [&](uint32_t (&v)[32], int ch) {
@@ -869,7 +877,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
             const uint64_t b = fadd2(e2[8 * g + 4 + h], e2[8 * g + 6 + h]);
             rp2[2 * g + h] = fadd2(rp2[2 * g + h], fadd2(a, b));
           }
-        if (STASH && !dbg_nostage) {
+        if constexpr (STASH) {
           // E~ = e' tau_j, packed to fp16 and staged through stmatrix in the TMA store's swizzled layout
           uint8_t* slab = staging + (slice * 2 + (ch >> 1)) * kSlabBytes;
           const uint32_t slab_addr = smem_u32(slab) + st_row + ((ch & 1) ? st_chunk1 : st_chunk0);
@@ -933,7 +941,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
           if constexpr (STASH) {
             if (slice_tid == 0) {
               const int gcol = n0 + col0 + (ch >> 1) * 64;
-              if (gcol < P.rows_global && !dbg_nostore)
+              if (gcol < P.rows_global)
                 tma_store_2d(&P.maps[P.store_map[p]], staging + (slice * 2 + (ch >> 1)) * kSlabBytes, gcol, m0);
               tma_store_commit();
             }
@@ -941,7 +949,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
         }
       }
       // column statistics of this slice: the four lane quarters are complete after the last slab barrier
-      if (n0 + my_col < P.rows_global && !dbg_nostat)
+      if (n0 + my_col < P.rows_global)
         P.col_part[(static_cast<size_t>(p) * P.nti + ti) * P.rows_global + n0 + my_col] =
             (colacc[acc][0][my_col] + colacc[acc][1][my_col]) + (colacc[acc][2][my_col] + colacc[acc][3][my_col]);
       {
@@ -954,7 +962,7 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
         }
         int r;
         const float rsum = frag_row_sum(rp, lane, r);
-        if (wrow0 + r < P.rows_local && !dbg_nostat)
+        if (wrow0 + r < P.rows_local)
           P.row_part[(static_cast<size_t>(p) * P.ntj * 2 + tj * 2 + slice) * P.rows_local + wrow0 + r] = rsum;
       }
       if (slice_tid == 0 && slice == 0) P.tile_ref[(static_cast<size_t>(p) * P.nti + ti) * P.ntj + tj] = 0.f;
@@ -988,25 +996,23 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) backward_tiles_kernel(const _
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == EW) {
-    if (lane == 0) {
-      RingState rs;
-      for (int t = cluster_id; t < total; t += num_clusters) {
-        const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
-        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
-      }
+    const bool elected = elect_one();
+    RingState rs;
+    for (int t = cluster_id; t < total; t += num_clusters) {
+      const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
+      producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs, elected);
     }
-    __syncwarp();
   } else if (warp == EW + 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the leader CTA issues the MMAs of the pair
+      const bool elected = elect_one();
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
         const Tile tile = decode_similarity<CG>(t, nti_c, P.ntj);
         const int acc = it & 1;
-        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1, elected);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int slice = warp >> 2;
@@ -1186,25 +1192,23 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_tiles_kernel(const __gri
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == EW) {
-    if (lane == 0) {
-      RingState rs;
-      for (int t = cluster_id; t < total; t += num_clusters) {
-        const Tile tile = decode_gemm<CG>(P, t);
-        producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs);
-      }
+    const bool elected = elect_one();
+    RingState rs;
+    for (int t = cluster_id; t < total; t += num_clusters) {
+      const Tile tile = decode_gemm<CG>(P, t);
+      producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs, elected);
     }
-    __syncwarp();
   } else if (warp == EW + 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // the leader CTA issues the MMAs of the pair
+      const bool elected = elect_one();
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
         const Tile tile = decode_gemm<CG>(P, t);
         const int acc = it & 1;
-        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1);
+        mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1, elected);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int slice = warp >> 2;
@@ -1306,32 +1310,25 @@ __device__ __forceinline__ Tile decode_wide(const GemmParams& P, int t) {
   return r;
 }
 
-// NP = 1: clusters of one CTA pair.  NP = 2 (jobs with exactly two n tiles): clusters of two pairs that work on the two
-// n tiles of the same 256 rows; every CTA loads one 64-row half of its A tile and multicasts it to the CTA of the other
-// pair that needs the same rows, so each A byte leaves L2 (and HBM) once per role and the pairs advance in lockstep.
-template <int EW, int NP>
+template <int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid_constant__ GemmParams P) {
   constexpr int S = EW / 4;
-  constexpr int CL = 2 * NP;  // CTAs per cluster
   __shared__ WideBarriers bars;
   uint8_t* smem = aligned_dyn_smem();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const uint32_t half = rank & 1u;      // which 128 rows of the pair's 256
-  const uint32_t pair = rank >> 1;      // which n tile (NP == 2)
-  const uint32_t leader = rank & ~1u;   // CTA that issues this pair's MMAs
-  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
-  const int total = P.total_tiles / NP;  // NP == 2: one unit = both n tiles of (job, row tile, k split)
+  const uint32_t half = cluster_ctarank();  // which 128 rows of the pair's 256; CTA 0 issues the MMAs
+  const int cluster_id = blockIdx.x / 2, num_clusters = gridDim.x / 2;
+  const int total = P.total_tiles;
   const int wn = P.wn;
-  const int n2 = wn - 256;                       // columns of the second MMA (0, 128 or 256)
+  const int n2 = wn - 256;                          // columns of the second MMA (0, 128 or 256)
   const int stage_bytes = A_STAGE_BYTES + wn * 64;  // A 128 x 64 + B (wn / 2) x 64 fp16
   const int stages = P.stages;
 
   if (warp == EW && lane == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bars.full[i], 1);
-      mbar_init(&bars.empty[i], NP);  // one commit per pair whose loads write this CTA's slot
+      mbar_init(&bars.empty[i], 1);
     }
     mbar_init(&bars.tmem_full, 1);
     mbar_init(&bars.tmem_empty, 2 * EW);
@@ -1345,109 +1342,94 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars.tmem_base);
+  const uint32_t smem0 = smem_u32(smem);
 
-  auto decode = [&](int u) {
-    Tile t = decode_wide(P, NP == 1 ? u : 2 * u);
-    if (NP == 2) {
-      t.tj = static_cast<int>(pair);
-      t.n0 = t.tj * wn;
-    }
-    return t;
-  };
-
-  if (warp == EW) {
-    if (lane == 0) {
-      RingState rs;
-      const uint32_t full0 = mapa(smem_u32(&bars.full[0]), leader);
-      const uint16_t mc_mask = static_cast<uint16_t>(0b0101u << half);  // the CTAs holding the same 128 rows
-      for (int u = cluster_id; u < total; u += num_clusters) {
-        const Tile tile = decode(u);
-        const Job& job = P.jobs[tile.job];
-        const int m0 = tile.m0 + static_cast<int>(half) * BM;
-        const int nb1 = tile.n0 + static_cast<int>(half) * 128;             // this CTA's columns of MMA 1
-        const int nb2 = tile.n0 + 256 + static_cast<int>(half) * (n2 / 2);  // ... of MMA 2
-        for (int s = 0; s < job.nseg; ++s) {
-          const Segment seg = job.seg[s];
-          const CUtensorMap* ma = P.maps + seg.map_a;
-          const CUtensorMap* ma64 = P.maps + seg.map_a64;
-          const CUtensorMap* mb = P.maps + seg.map_b;
-          int kb_lo, kb_hi;
-          split_range(seg.num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
-          for (int kb = kb_lo; kb < kb_hi; ++kb) {
-            mbar_wait_bounded<NP == 2>(&bars.empty[rs.stage], rs.phase ^ 1u, 1);
-            uint8_t* sa = smem + rs.stage * stage_bytes;
-            uint8_t* sb = sa + A_STAGE_BYTES;
+  if (warp == EW) {  // TMA producer (convergent warp code, one elected lane issues)
+    const bool elected = elect_one();
+    RingState rs;
+    const uint32_t full_loc0 = smem_u32(&bars.full[0]);
+    const uint32_t full_sig0 = mapa(full_loc0, 0);
+    for (int u = cluster_id; u < total; u += num_clusters) {
+      const Tile tile = decode_wide(P, u);
+      const Job& job = P.jobs[tile.job];
+      const int m0 = tile.m0 + static_cast<int>(half) * BM;
+      const int nb1 = tile.n0 + static_cast<int>(half) * 128;             // this CTA's columns of MMA 1
+      const int nb2 = tile.n0 + 256 + static_cast<int>(half) * (n2 / 2);  // ... of MMA 2
+      for (int s = 0; s < job.nseg; ++s) {
+        const CUtensorMap* ma = P.maps + job.seg[s].map_a;
+        const CUtensorMap* mb = P.maps + job.seg[s].map_b;
+        const int a_mn = job.seg[s].a_mn;
+        int kb_lo, kb_hi;
+        split_range(job.seg[s].num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          mbar_wait_bounded<false>(&bars.empty[rs.stage], rs.phase ^ 1u, 1);
+          if (elected) {
+            const uint32_t sa = smem0 + rs.stage * stage_bytes;
+            const uint32_t sb = sa + A_STAGE_BYTES;
+            const uint32_t bar = full_sig0 + rs.stage * 8;
             const int k = kb * BK;
-            const uint32_t bar = full0 + rs.stage * 8;
-            if (half == 0) mbar_expect_tx(&bars.full[rs.stage], 2 * stage_bytes);
-            if constexpr (NP == 1) {
-              if (!seg.a_mn) {
-                tma_load_2d_2sm(sa, ma, bar, k, m0);
-              } else {
-                tma_load_2d_2sm(sa, ma, bar, m0, k);
-                tma_load_2d_2sm(sa + MN_BOX_BYTES, ma, bar, m0 + 64, k);
-              }
+            if (half == 0) mbar_expect_tx_u32(full_loc0 + rs.stage * 8, 2 * stage_bytes);
+            if (!a_mn) {
+              tma_load_2d_2sm_u32(sa, ma, bar, k, m0);
             } else {
-              // this CTA's 64-row share of the A tile, delivered to both CTAs that hold these 128 rows
-              uint8_t* dst = sa + pair * MN_BOX_BYTES;
-              const int mrow = m0 + static_cast<int>(pair) * 64;
-              if (!seg.a_mn) tma_load_2d_2sm_mc(dst, ma64, bar, k, mrow, mc_mask);
-              else tma_load_2d_2sm_mc(dst, ma, bar, mrow, k, mc_mask);
+              tma_load_2d_2sm_u32(sa, ma, bar, m0, k);
+              tma_load_2d_2sm_u32(sa + MN_BOX_BYTES, ma, bar, m0 + 64, k);
             }
-            tma_load_2d_2sm(sb, mb, bar, nb1, k);
-            tma_load_2d_2sm(sb + MN_BOX_BYTES, mb, bar, nb1 + 64, k);
-            for (int g = 0; g < n2 / 128; ++g)
-              tma_load_2d_2sm(sb + (2 + g) * MN_BOX_BYTES, mb, bar, nb2 + g * 64, k);
-            rs.advance(stages);
+            tma_load_2d_2sm_u32(sb, mb, bar, nb1, k);
+            tma_load_2d_2sm_u32(sb + MN_BOX_BYTES, mb, bar, nb1 + 64, k);
+            if (n2 >= 128) tma_load_2d_2sm_u32(sb + 2 * MN_BOX_BYTES, mb, bar, nb2, k);
+            if (n2 >= 256) tma_load_2d_2sm_u32(sb + 3 * MN_BOX_BYTES, mb, bar, nb2 + 64, k);
           }
+          rs.advance(stages);
         }
       }
     }
-    __syncwarp();
   } else if (warp == EW + 1) {
-    if (lane == 0 && half == 0) {
+    if (half == 0) {  // MMA issuer (leader CTA; convergent warp code, one elected lane issues)
+      const bool elected = elect_one();
       RingState rs;
       int it = 0;
-      const uint16_t all_mask = NP == 2 ? 0b1111 : 0b11;
-      const uint16_t pair_mask = static_cast<uint16_t>(0b11u << (2 * pair));
+      const uint32_t empty0 = smem_u32(&bars.empty[0]);
+      const uint32_t tfull = smem_u32(&bars.tmem_full);
+      constexpr uint32_t hi = smem_desc_hi_sw128(1024);
       for (int u = cluster_id; u < total; u += num_clusters, ++it) {
-        const Tile tile = decode(u);
+        const Tile tile = decode_wide(P, u);
         const Job& job = P.jobs[tile.job];
         mbar_wait_bounded<false>(&bars.tmem_empty, (it & 1) ^ 1u, 4);  // the epilogue has drained the accumulator
         tc_fence_after();
         uint32_t accumulate = 0;
         for (int s = 0; s < job.nseg; ++s) {
-          const Segment seg = job.seg[s];
-          const uint32_t idesc1 = make_idesc_f16(2 * BM, 256, 0, seg.a_mn, 1);
-          const uint32_t idesc2 = make_idesc_f16(2 * BM, n2 > 0 ? n2 : 256, 0, seg.a_mn, 1);
+          const int a_mn = job.seg[s].a_mn;
+          const uint32_t idesc1 = make_idesc_f16(2 * BM, 256, 0, a_mn, 1);
+          const uint32_t idesc2 = make_idesc_f16(2 * BM, n2 > 0 ? n2 : 256, 0, a_mn, 1);
+          const uint32_t a_lbo = a_mn ? OperandDesc<true>::kLbo : OperandDesc<false>::kLbo;
+          const uint32_t a_step = a_mn ? OperandDesc<true>::kStep : OperandDesc<false>::kStep;
           int kb_lo, kb_hi;
-          split_range(seg.num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+          split_range(job.seg[s].num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
           for (int kb = kb_lo; kb < kb_hi; ++kb) {
-            mbar_wait_bounded<NP == 2>(&bars.full[rs.stage], rs.phase, 2);
+            mbar_wait_bounded<false>(&bars.full[rs.stage], rs.phase, 2);
             tc_fence_after();
-            const uint32_t a_base = smem_u32(smem + rs.stage * stage_bytes);
-            const uint32_t b_base = a_base + A_STAGE_BYTES;
+            if (elected) {
+              const uint32_t a_lo = smem_desc_lo(smem0 + rs.stage * stage_bytes, a_lbo);
+              const uint32_t b_lo = smem_desc_lo(smem0 + rs.stage * stage_bytes + A_STAGE_BYTES, MN_BOX_BYTES);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t adesc = seg.a_mn ? make_smem_desc_sw128(a_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024)
-                                              : make_smem_desc_sw128(a_base + k * (UMMA_K * 2), 16, 1024);
-              const uint64_t bdesc1 = make_smem_desc_sw128(b_base + k * (UMMA_K * 128), MN_BOX_BYTES, 1024);
-              umma_f16<2>(tmem_base, adesc, bdesc1, idesc1, accumulate);
-              if (n2 > 0) {
-                const uint64_t bdesc2 =
-                    make_smem_desc_sw128(b_base + 2 * MN_BOX_BYTES + k * (UMMA_K * 128), MN_BOX_BYTES, 1024);
-                umma_f16<2>(tmem_base + 256, adesc, bdesc2, idesc2, accumulate);
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adesc = smem_desc_join(a_lo + k * a_step, hi);
+                umma_f16<2>(tmem_base, adesc, smem_desc_join(b_lo + k * OperandDesc<true>::kStep, hi), idesc1, accumulate);
+                if (n2 > 0)
+                  umma_f16<2>(tmem_base + 256, adesc,
+                              smem_desc_join(b_lo + ((2 * MN_BOX_BYTES) >> 4) + k * OperandDesc<true>::kStep, hi), idesc2,
+                              accumulate);
+                accumulate = 1;
               }
-              accumulate = 1;
+              umma_commit_2sm_u32(empty0 + rs.stage * 8, 0b11);  // frees the slot in both CTAs
             }
-            umma_commit_2sm(&bars.empty[rs.stage], all_mask);  // frees the slot in every CTA whose loads fill it
             rs.advance(stages);
           }
         }
-        umma_commit_2sm(&bars.tmem_full, pair_mask);
+        if (elected) umma_commit_2sm_u32(tfull, 0b11);
       }
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int slice = warp >> 2;
@@ -1461,7 +1443,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid
     }
     int it = 0;
     for (int u = cluster_id; u < total; u += num_clusters, ++it) {
-      const Tile tile = decode(u);
+      const Tile tile = decode_wide(P, u);
       const int j = tile.job;
       const bool accumulate_out = P.jobs[j].ksplits > 1;
       const int row = tile.m0 + static_cast<int>(half) * BM + q * 32 + lane;
@@ -1482,7 +1464,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid
           __syncwarp();
           if (lane == 0) {
             if (half == 0) mbar_arrive(&bars.tmem_empty);
-            else mbar_arrive_cluster(&bars.tmem_empty, leader);
+            else mbar_arrive_cluster(&bars.tmem_empty, 0);
           }
         }
         if (row_ok) {
@@ -1505,7 +1487,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid
     }
   }
   tc_fence_before();
-  cluster_sync();  // no CTA of the cluster may exit while another can still signal its barriers
+  cluster_sync();  // no CTA of the pair may exit while the other can still signal its barriers
   if (warp == EW + 1) {
     tc_fence_after();
     tmem_dealloc<2>(tmem_base, 512);
@@ -1614,24 +1596,8 @@ int launch_gemm_wide(const GemmParams& p, int ew, cudaStream_t stream) {
     return SCLIP_ERR_ARGUMENT;
   }
   const int smem = p.stages * (A_STAGE_BYTES + p.wn * 64) + 1024;
-  // SCLIP_MCAST=1 (experiment, off by default): two pairs per cluster share the A tiles by TMA multicast when every
-  // job has exactly two n tiles.  Measured on B200 (32768 x 768 x 32768): 850 TFLOP/s against 1355 TFLOP/s for
-  // independent pairs.  The same four-CTA clusters with every pair loading its own A copy (lockstep only) reach 830:
-  // it is the coupling of two pairs through one set of barriers that costs, not the multicast.  Pacing independent
-  // partner clusters through progress counters in global memory (so that the second reader of an A line hits L2) was
-  // also tried: the polling stalls the producer and the DRAM traffic did not drop (18.5 GB against 19.1 GB).
-  static const bool mcast_on = [] {
-    const char* e = getenv("SCLIP_MCAST");
-    return e != nullptr && e[0] == '1';
-  }();
-  bool two = mcast_on && p.total_tiles % 2 == 0;
-  for (int j = 0; j < p.njobs; ++j) two = two && p.jobs[j].n_tiles == 2;
-  if (two) {
-    if (ew == 16) return launch_persistent(gemm_wide_kernel<16, 2>, p, 4, 16, smem, p.total_tiles / 2, stream);
-    return launch_persistent(gemm_wide_kernel<8, 2>, p, 4, 8, smem, p.total_tiles / 2, stream);
-  }
-  if (ew == 16) return launch_persistent(gemm_wide_kernel<16, 1>, p, 2, 16, smem, p.total_tiles, stream);
-  return launch_persistent(gemm_wide_kernel<8, 1>, p, 2, 8, smem, p.total_tiles, stream);
+  if (ew == 16) return launch_persistent(gemm_wide_kernel<16>, p, 2, 16, smem, p.total_tiles, stream);
+  return launch_persistent(gemm_wide_kernel<8>, p, 2, 8, smem, p.total_tiles, stream);
 }
 
 }  // namespace sclip

@@ -49,8 +49,11 @@ def _scaled_cosine(a: torch.Tensor, b: torch.Tensor, log_scale: torch.Tensor) ->
     (ZS_task.py:338,344 and the ``return_logits`` consumers ZS_image_task.py:1479, ZS_audio_task.py:195) run under
     ``torch.no_grad()`` on the GPU: those go through the library's normalise + tile kernels.  With autograd enabled, or
     on the CPU, the reference's own three statements are executed unchanged."""
-    if a.is_cuda and not torch.is_grad_enabled() and a.dtype in (torch.float32, torch.bfloat16) and a.shape[1] % 8 == 0:
-        return cosine_logits(a, b, log_scale)
+    fused = (a.is_cuda and b.is_cuda and a.device == b.device and a.dtype == b.dtype and not torch.is_grad_enabled()
+             and a.dtype in (torch.float32, torch.bfloat16) and a.dim() == 2 and b.dim() == 2
+             and a.shape[1] == b.shape[1] and a.shape[1] % 8 == 0)
+    if fused:
+        return cosine_logits(a, b, log_scale, out_dtype=a.dtype)  # contiguous, dtype of the embeddings like the reference
     return torch.matmul(_unit(a), _unit(b).t()) * log_scale.exp()
 
 

@@ -137,6 +137,26 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _on_device:
+    """Make the tensors' device the current CUDA device for the duration of a call.  The reference driver spawns its ranks
+    with mp.spawn, moves the model with `.to(rank)` and never calls torch.cuda.set_device (main_pretraining.py:64,137-138),
+    so on rank r > 0 the current device is still 0 while the embeddings live on cuda:r.  Streams, events, tensor-map
+    encodes and kernel launches of the library all go to the current device: select the tensors' one first."""
+
+    def __init__(self, t: torch.Tensor):
+        self._ctx = torch.cuda.device(t.device) if t.is_cuda else None
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            return self._ctx.__exit__(*exc)
+        return False
+
+
 class _Workspace:
     """One workspace blob + typed views of the sub-buffers the host touches."""
 
@@ -181,6 +201,8 @@ class _SymmWorkspace(_Workspace):
 
 
 _P2P_FAILED = False
+_MAX_PEERS = 16  # SCLIP_MAX_PEERS (include/sclip.h)
+_ROWS_CHECKED = set()
 
 
 def _try_symm_workspace(pb: Problem, device, group):
@@ -221,6 +243,12 @@ def _use_p2p(cfg, img) -> bool:
     if cfg.process_group is None or not img.is_cuda or _BACKEND.allows_cpu:
         return False
     if cfg.transport == "nccl":
+        return False
+    import torch.distributed as dist
+
+    if dist.get_world_size(cfg.process_group) > _MAX_PEERS:  # SCLIP_MAX_PEERS: the pull kernels take at most 16 ranks
+        if cfg.transport == "p2p":
+            raise _lib.SclipError(f"transport='p2p' supports at most {_MAX_PEERS} ranks")
         return False
     if cfg.transport == "p2p":
         return True
@@ -269,16 +297,22 @@ _POOL = _Pool()
 
 
 class _Lease:
+    """A workspace held from a forward until its backward has run (released explicitly there; `__del__` only covers
+    graphs that are dropped without a backward)."""
+
     def __init__(self, ws: _Workspace):
         self.ws = ws
 
-    def __del__(self):
+    def release(self):
         ws, self.ws = self.ws, None
         if ws is not None:
-            try:
-                _POOL.release(ws)
-            except Exception:
-                pass
+            _POOL.release(ws)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def _make_problem(img: torch.Tensor, cfg: TriContrastiveConfig) -> Tuple[Problem, int, int]:
@@ -289,6 +323,16 @@ def _make_problem(img: torch.Tensor, cfg: TriContrastiveConfig) -> Tuple[Problem
     if cfg.process_group is not None:
         world = dist.get_world_size(cfg.process_group)
         rank = dist.get_rank(cfg.process_group)
+        # the row-strip layout assumes equal shards (rows_global = world * rows_local): checked once per shape
+        key = (id(cfg.process_group), rows)
+        if world > 1 and key not in _ROWS_CHECKED:
+            counts = torch.tensor([rows, -rows], device=img.device, dtype=torch.int64)
+            dist.all_reduce(counts, op=dist.ReduceOp.MAX, group=cfg.process_group)
+            lo_hi = counts.tolist()
+            if lo_hi[0] != rows or -lo_hi[1] != rows:
+                raise ValueError(f"the sharded contrastive objective needs the same number of rows on every rank "
+                                 f"(this rank: {rows}, range over ranks: {-lo_hi[1]}..{lo_hi[0]}); use drop_last=True")
+            _ROWS_CHECKED.add(key)
     if img.dtype == torch.float32:
         dtype = SCLIP_F32
     elif img.dtype == torch.bfloat16:
@@ -688,9 +732,10 @@ class _TriContrastive(torch.autograd.Function):
     def forward(ctx, img, txt, aud, t3, cfg):
         img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
         pb, _, _ = _make_problem(img, cfg)
-        ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
-        lease = _Lease(ws)
-        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
+        with _on_device(img):
+            ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
+            lease = _Lease(ws)
+            loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
         ctx.save_for_backward(img, txt, aud, t3)
         ctx.lease = lease
         ctx.cfg = cfg
@@ -701,11 +746,14 @@ class _TriContrastive(torch.autograd.Function):
     def backward(ctx, g3):
         img, txt, aud, t3 = ctx.saved_tensors
         ws = ctx.lease.ws
-        if ctx.stashed and not ws.stashed:
-            raise _lib.SclipError("the contrastive objective was already back-propagated once: its stashed tiles are "
-                                  "converted in place and cannot serve a second backward (retain_graph)")
+        if ws is None or (ctx.stashed and not ws.stashed):
+            raise _lib.SclipError("the contrastive objective was already back-propagated once: its workspace (stashed "
+                                  "tiles converted in place) cannot serve a second backward (retain_graph)")
         g3 = g3.to(torch.float32).contiguous()
-        dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, ctx.cfg)
+        with _on_device(img):
+            dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, ctx.cfg)
+        # the workspace goes back to the pool here, on the stream that ran the backward (not at garbage-collection time)
+        ctx.lease.release()
         if not ctx.cfg.grads_fp32:
             dimg, dtxt, daud = dimg.to(img.dtype), dtxt.to(img.dtype), daud.to(img.dtype)
         return dimg, dtxt, daud, dt3, None
@@ -724,11 +772,12 @@ def fused_tri_contrastive(img: torch.Tensor, txt: torch.Tensor, aud: torch.Tenso
     else:  # eval loops run under torch.no_grad() (main_pretraining.py:192-210): nothing is kept for backward
         img, txt, aud = img.contiguous(), txt.contiguous(), aud.contiguous()
         pb, _, _ = _make_problem(img, cfg)
-        ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
-        try:
-            loss3 = _forward_impl(ws, img.detach(), txt.detach(), aud.detach(), t3.detach(), cfg)
-        finally:
-            _POOL.release(ws)
+        with _on_device(img):
+            ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
+            try:
+                loss3 = _forward_impl(ws, img.detach(), txt.detach(), aud.detach(), t3.detach(), cfg)
+            finally:
+                _POOL.release(ws)
     return loss3[0], loss3[1], loss3[2]
 
 
@@ -737,12 +786,13 @@ def forward_backward_raw(img, txt, aud, t3, g3, config: Optional[TriContrastiveC
     cfg = config or _DEFAULT
     _check_inputs(img, txt, aud)
     pb, _, _ = _make_problem(img, cfg)
-    ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
-    try:
-        loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
-        dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, cfg)
-    finally:
-        _POOL.release(ws)
+    with _on_device(img):
+        ws = _POOL.acquire_sharded(pb, img.device, cfg.process_group, _use_p2p(cfg, img))
+        try:
+            loss3 = _forward_impl(ws, img, txt, aud, t3, cfg, keep=True)
+            dimg, dtxt, daud, dt3 = _backward_impl(ws, img, txt, aud, t3, g3, cfg)
+        finally:
+            _POOL.release(ws)
     return loss3, dimg, dtxt, daud, dt3
 
 
@@ -760,24 +810,26 @@ def gemm_f16(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = 
     if k != kb:
         raise ValueError("inner dimensions differ")
     c = torch.empty((m, n), dtype=torch.float32, device=a.device)
-    _lib.check(lib.sclip_gemm_f16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(c), n, m, n, k,
-                                  ctypes.c_float(alpha), _stream()), "sclip_gemm_f16")
+    with _on_device(a):
+        _lib.check(lib.sclip_gemm_f16(_ptr(a), a.stride(0), int(a_mn), _ptr(b), b.stride(0), int(b_mn), _ptr(c), n, m, n,
+                                      k, ctypes.c_float(alpha), _stream()), "sclip_gemm_f16")
     return c
 
 
-_SCRATCH = {}
-
-
-def cosine_logits(a: torch.Tensor, b: torch.Tensor, log_scale: torch.Tensor, math: str = "auto") -> torch.Tensor:
+def cosine_logits(a: torch.Tensor, b: torch.Tensor, log_scale: torch.Tensor, math: str = "auto",
+                  out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """``exp(log_scale) * unit(a) @ unit(b).T`` as a materialised (M, N) fp32 matrix -- the arithmetic of the reference's
     zero-shot scorers (``get_img_txt_sim_score`` / ``get_aud_txt_sim_score``, model.py:126-203) and of its
     ``return_logits`` branch (model.py:275-277) on the library's normalise + tile kernels.  Forward only (the reference
-    calls these under ``torch.no_grad()``: ZS_task.py:338,344); CUDA only, no CPU fallback."""
+    calls these under ``torch.no_grad()``: ZS_task.py:338,344); CUDA only, no CPU fallback.
+
+    Returns a contiguous (M, N) matrix, fp32 by default (what the kernel accumulates in); ``out_dtype=a.dtype`` gives
+    the reference's contract (logits in the dtype of the embeddings), which the ``Tri_CLIP`` mirror asks for."""
     lib = _lib.load()
     if not a.is_cuda or not b.is_cuda:
         raise _lib.SclipError("cosine_logits only runs on a CUDA (sm_100a) device and has no CPU fallback")
-    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or a.dtype != b.dtype:
-        raise ValueError("cosine_logits takes (M, D) and (N, D) matrices of one dtype")
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1] or a.dtype != b.dtype or a.device != b.device:
+        raise ValueError("cosine_logits takes (M, D) and (N, D) matrices of one dtype on one device")
     if a.dtype == torch.float32:
         dtype = SCLIP_F32
     elif a.dtype == torch.bfloat16:
@@ -792,15 +844,16 @@ def cosine_logits(a: torch.Tensor, b: torch.Tensor, log_scale: torch.Tensor, mat
     n = b.shape[0]
     need = ctypes.c_uint64()
     _lib.check(lib.sclip_cosine_logits_scratch(m, n, d, mode, byref(need)), "sclip_cosine_logits_scratch")
-    key = (a.device.index, int(need.value))
-    scratch = _SCRATCH.get(key)
-    if scratch is None:
+    with _on_device(a):
+        # scratch comes from the caching allocator per call: it is tied to the calling stream like any torch tensor
+        # (a process-wide cache keyed by size alone would be shared by concurrent calls on different streams)
         raw = torch.empty(int(need.value) + 256, dtype=torch.uint8, device=a.device)
         skew = (-raw.data_ptr()) % 256
-        scratch = _SCRATCH[key] = raw[skew:skew + int(need.value)]
-    ldc = (n + 3) // 4 * 4
-    out = torch.empty((m, ldc), dtype=torch.float32, device=a.device)
-    t = log_scale.detach().reshape(1).to(device=a.device, dtype=torch.float32)
-    _lib.check(lib.sclip_cosine_logits(_ptr(a), _ptr(b), _ptr(t), m, n, d, dtype, mode, _ptr(scratch), _ptr(out), ldc,
-                                       _stream()), "sclip_cosine_logits")
-    return out[:, :n]
+        scratch = raw[skew:skew + int(need.value)]
+        ldc = (n + 3) // 4 * 4
+        out = torch.empty((m, ldc), dtype=torch.float32, device=a.device)
+        t = log_scale.detach().reshape(1).to(device=a.device, dtype=torch.float32)
+        _lib.check(lib.sclip_cosine_logits(_ptr(a), _ptr(b), _ptr(t), m, n, d, dtype, mode, _ptr(scratch), _ptr(out),
+                                           ldc, _stream()), "sclip_cosine_logits")
+        res = out if ldc == n else out[:, :n].contiguous()
+        return res if out_dtype in (None, torch.float32) else res.to(out_dtype)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SCLIP_ABI_VERSION 1
+#define SCLIP_ABI_VERSION 2
 
 typedef enum sclip_status {
   SCLIP_OK = 0,
@@ -94,7 +94,13 @@ typedef struct sclip_layout {
   uint64_t fac_row;       /* [3][2][rows_local rounded up to 64] fp32 row factors of the stash -> G' conversion */
   uint64_t fac_col;       /* [3][2][rows_global rounded up to 64] fp32 column factors                           */
   uint64_t dot_part;      /* [3][ceil(rows_local/8)] fp32 partial sums of <xhat, dxhat> (stash mode dlogit_scale) */
-  uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed) */
+  uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed);
+                             cleared by sclip_prologue, read back by sclip_read_status                            */
+  uint64_t rowterm_part;  /* [3][ceil(rows_local/64)] fp64 partial sums of the row term of the loss
+                             [read by the peers in sclip_forward_loss_peers]                                      */
+  uint64_t sync;          /* [64] int32 flags and counters that live across calls (per-source-rank "shard landed"
+                             epochs, block counters).  THE OWNER ZEROES THIS AREA ONCE when the workspace is
+                             allocated; the library never needs it cleared again.                                 */
   int32_t row_tiles;      /* ceil(rows_local / 128)   */
   int32_t col_tiles;      /* ceil(rows_global / 256)  */
   int32_t ld_g;           /* leading dimension (elements) of grad_tiles */
@@ -112,9 +118,12 @@ int sclip_plan(const sclip_problem* problem, sclip_layout* layout);
 /* ---- forward (model.py:248-272) -------------------------------------------------------------- */
 
 /* x / x.norm(p=2, dim=-1, keepdim=True) (model.py:248-250, no epsilon) for this rank's rows of the
- * three modalities, rounded to the tensor-core operand format and written at row_offset of `xhat`. */
+ * three modalities, rounded to the tensor-core operand format and written at row_offset of `xhat`.
+ * flags & SCLIP_PRO_DIAG (SCLIP_MATH_F16, needs t3): the same kernel also writes the positive-pair logits L_ii of
+ * this rank's rows into diag_all -- what a forward with SCLIP_FWD_STASH needs; t3 may be NULL otherwise. */
+#define SCLIP_PRO_DIAG 1
 int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
-                   void* stream);
+                   const float* t3, int flags, void* stream);
 
 /* The three similarity strips (rows_local x rows_global each) with the exp / row-sum / column-sum /
  * diagonal epilogue (model.py:254-265 and the softmax statistics of model.py:52-58); logits are never
@@ -132,13 +141,22 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
 /* flags & SCLIP_FWD_WRAP: the column tiles [col_tile_begin, col_tile_end) are taken modulo col_tiles (a range of
  * ranks' columns that wraps around the end of the global batch); col_tile_end - col_tile_begin <= col_tiles. */
 #define SCLIP_FWD_WRAP 2
+/* flags & SCLIP_FWD_WAIT_PEERS (world > 1, rows_local a multiple of 256, the full column range): ONE launch covers
+ * every column; the tiles are taken rank by rank -- this rank's own columns first, then those of rank + 1, rank + 2,
+ * ... -- and the kernel itself waits (acquire loads of the per-rank "landed" flags in `sync`) until
+ * sclip_pull_shards(..., epoch) has completed a rank's shard before touching its columns.  The pulls run concurrently
+ * on another stream; give them SMs with max_sms.  `epoch` must be the value passed to that sclip_pull_shards call
+ * (use a counter that grows by one per forward). */
+#define SCLIP_FWD_WAIT_PEERS 4
+/* max_sms > 0: the persistent grid takes at most that many SMs, leaving the rest to concurrently running
+ * communication kernels (0 = all). */
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
-                             int col_tile_begin, int col_tile_end, int flags, void* stream);
+                             int col_tile_begin, int col_tile_end, int flags, int max_sms, int epoch, void* stream);
 
 /* Positive-pair logits L_ii of this rank's rows for the three pairs, written into diag_all at row_offset. */
 int sclip_forward_diag(const sclip_problem* problem, void* ws, const float* t3, void* stream);
 
-/* Merge the per-tile statistics into lse_row and lse_col_local. */
+/* Merge the per-tile statistics into lse_row, lse_col_local and the partial sums of the loss' row term. */
 int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream);
 
 /* lse_col = logsumexp over ranks of `col_lse_all` ([world][3][rows_global], NULL => this rank's own
@@ -147,6 +165,13 @@ int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream);
  * written to the workspace and to loss3 (device, 3 floats).  Summed over ranks it is clip_loss. */
 int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_lse_all, float* loss3,
                        void* stream);
+
+/* Peer-memory variant (see "peer-memory exchanges" below): one kernel reads every rank's lse_col_local and row-term
+ * partial sums straight from the peers' workspaces (after a barrier behind sclip_forward_reduce), merges lse_col and
+ * computes the COMPLETE three losses -- identical on every rank -- into loss3.  Replaces the all-gather of the column
+ * statistics, sclip_forward_loss and the all-reduce of the loss shares. */
+int sclip_forward_loss_peers(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3,
+                             void* stream);
 
 /* ---- backward (autograd of model.py:248-272) --------------------------------------------------- */
 
@@ -172,12 +197,9 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
 #define SCLIP_ROLE_BOTH 0
 #define SCLIP_ROLE_COLUMN 1
 #define SCLIP_ROLE_ROW 2
+/* max_sms > 0: at most that many SMs (see sclip_forward_tiles_cols). */
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
-                              int flags, void* stream);
-
-/* Process-wide launch option: the persistent tile kernels use at most max_sms SMs (0 = all), leaving the rest to
- * concurrently running communication kernels.  Returns the previous value. */
-int sclip_set_max_sms(int max_sms);
+                              int max_sms, void* stream);
 
 /* Backward of the normalisation: d x = (d - xhat <xhat, d>) / ||x|| with d = dxhat_row (+ col_contrib, the
  * reduce-scattered column-role gradients [3][rows_local][dim] fp32, NULL when world == 1), times grad_mult
@@ -210,26 +232,28 @@ int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, in
 
 /* Pull all-gather: copy the normalised operand shards (and their positive-pair logits) of the `count` ranks
  * (rank + first + i) % world, i in [0, count), into this rank's xhat / diag_all.  At most max_blocks thread blocks of
- * block_threads (<= 1024) threads: either big blocks on SMs left free by sclip_set_max_sms, or 256-thread blocks, one
- * per SM, which fit beside a resident persistent tile CTA. */
+ * block_threads (<= 1024) threads: either big blocks on SMs left free by max_sms, or 256-thread blocks, one
+ * per SM, which fit beside a resident persistent tile CTA.
+ * The shards complete one after the other in that order; when a shard is complete the kernel publishes
+ * landed[source rank] = epoch in `sync` (release), which forward tiles launched with SCLIP_FWD_WAIT_PEERS acquire. */
 int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
-                      int max_blocks, int block_threads, void* stream);
-
-/* col_lse_all[r][3][rows_global] = rank r's lse_col_local (the input of sclip_forward_loss). */
-int sclip_pull_col_lse(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* col_lse_all,
-                       void* stream);
-
-/* loss3[p] = sum over ranks of loss_part[p]: every rank ends up with the global-batch losses. */
-int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3, void* stream);
+                      int max_blocks, int block_threads, int epoch, void* stream);
 
 /* Pull reduce-scatter: col_contrib[m][i][:] = sum over ranks r (rank order) of rank r's dxhat_col[m][row_offset + i][:]
  * -- the column-role gradients of this rank's rows, ready for sclip_backward_finish. */
 int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* const* peer_ws, int max_blocks,
                            int block_threads /* <= 512 */, void* stream);
 
+/* Copy the four device status words of the workspace to the host (synchronises `stream`).  status_host[0] != 0: a row
+ * or column log-sum-exp of the last forward was not finite (non-finite embeddings, or exp(logit_scale) beyond what
+ * fp32 can hold); the losses are then non-finite too. */
+int sclip_read_status(const sclip_problem* problem, void* ws, int32_t* status_host, void* stream);
+
 /* ---- single-GPU convenience (world == 1): the whole tail in two calls ---------------------------
- * keep_for_backward != 0: sclip_backward will follow on the same workspace (SCLIP_MATH_F16 then stashes in the
- * forward and skips the recomputation); 0: forward only (evaluation loops). */
+ * keep_for_backward != 0: sclip_backward will follow on the same workspace.  With SCLIP_MATH_F16 and dim >= 640 the
+ * forward then stashes its tiles and the backward converts them (4 bytes of HBM traffic per logit instead of 2 dim
+ * flop: the measured crossover); otherwise the backward recomputes the similarities.  0: forward only (evaluation
+ * loops).  A stash serves ONE backward: a second sclip_backward on the same forward returns SCLIP_ERR_ARGUMENT. */
 int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                   const float* t3, int keep_for_backward, float* loss3, void* stream);
 int sclip_backward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,

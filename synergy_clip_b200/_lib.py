@@ -11,6 +11,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsclip.so")
 
+ABI_VERSION = 2
 SCLIP_F32, SCLIP_BF16 = 0, 1
 MATH_F16, MATH_F16X3 = 0, 1
 
@@ -32,7 +33,7 @@ class Layout(Structure):
     _fields_ = [(name, c_uint64) for name in (
         "total_bytes", "xhat", "xhat_lo", "inv_norm", "row_part", "col_part", "tile_ref", "diag", "lse_row",
         "lse_col_local", "lse_col", "row_inv", "col_sum_local", "col_inv", "loss_part", "grad_tiles", "grad_tiles_lo", "dt_part", "dxhat_row", "dxhat_col",
-        "col_contrib", "diag_all", "fac_row", "fac_col", "dot_part", "status")] + [("row_tiles", c_int32), ("col_tiles", c_int32), ("ld_g", c_int32), ("reserved", c_int32)]
+        "col_contrib", "diag_all", "fac_row", "fac_col", "dot_part", "status", "rowterm_part", "sync")] + [("row_tiles", c_int32), ("col_tiles", c_int32), ("ld_g", c_int32), ("reserved", c_int32)]
 
 
 class SclipError(RuntimeError):
@@ -44,9 +45,10 @@ _PROTOTYPES = {
     "sclip_last_error": (c_char_p, []),
     "sclip_kernel_launches": (ctypes.c_longlong, []),
     "sclip_plan": (c_int, [POINTER(Problem), POINTER(Layout)]),
-    "sclip_prologue": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sclip_prologue": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "sclip_forward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p]),
-    "sclip_forward_tiles_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sclip_forward_tiles_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
     "sclip_forward_diag": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p]),
     "sclip_backward_scale": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_forward_reduce": (c_int, [POINTER(Problem), c_void_p, c_void_p]),
@@ -54,16 +56,15 @@ _PROTOTYPES = {
     "sclip_backward_tiles": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_gemms": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_backward_gemms_role": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "sclip_set_max_sms": (c_int, [c_int]),
     "sclip_backward_finish": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "sclip_forward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                               c_void_p]),
     "sclip_backward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "sclip_pull_shards": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "sclip_pull_col_lse": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
-    "sclip_pull_loss": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sclip_pull_shards": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sclip_forward_loss_peers": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sclip_read_status": (c_int, [POINTER(Problem), c_void_p, POINTER(c_int32), c_void_p]),
     "sclip_pull_reduce_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "sclip_cosine_logits_scratch": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_uint64)]),
     "sclip_cosine_logits": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -91,7 +92,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.sclip_abi_version() != 1:
+    if lib.sclip_abi_version() != ABI_VERSION:
         raise SclipError("libsclip.so ABI version mismatch")
     _lib = lib
     return lib

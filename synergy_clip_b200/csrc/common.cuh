@@ -108,8 +108,16 @@ struct Workspace {  // resolved device pointers of one workspace blob
   float* fac_row;
   float* fac_col;
   float* dot_part;
+  double* rowterm_part;
   int* status;
+  int* sync;  // flags and counters that live across launches (zeroed once by the owner of the workspace)
 };
+
+// slots of the `sync` area (32-bit words)
+constexpr int kSyncLanded = 0;       // [SCLIP_MAX_PEERS] epoch of the last complete shard per source rank
+constexpr int kSyncArrived = 16;     // [SCLIP_MAX_PEERS] block counters of sclip_pull_shards
+constexpr int kSyncFinishDone = 32;  // block counter of sclip_backward_finish
+constexpr int kSyncWords = 64;
 
 struct FwdParams {
   CUtensorMap maps[kFwdMaps];
@@ -128,6 +136,13 @@ struct FwdParams {
   const float* diag_all;     // [3][rows_global] positive-pair logits (stash scaling)
   int stages;       // depth of the TMA ring
   int pair_filter;  // forward_tiles_kernel: skip the pairs forward_fast_kernel has taken (s < 44)
+  // SCLIP_FWD_WAIT_PEERS: tiles are taken rank by rank (this rank's own columns first, then rank + 1, ...) and the
+  // producer acquires landed[source rank] >= epoch before the first tile on a rank's columns
+  int wait_peers;
+  int tiles_per_rank;     // 256-column tiles per rank
+  int world, rank;
+  const int* landed;
+  int epoch;
   float acc_scale;  // accumulator -> cosine (1 in F16 mode, 2^-16 in F16X3 mode)
 };
 
@@ -168,20 +183,26 @@ struct GemmParams {
 
 // cg = 1: one CTA per tile of 128 rows; cg = 2: CTA pairs (cta_group::2) on tiles of 256 rows
 // ew = 8 | 16 epilogue warps per CTA
-int launch_forward_tiles(const FwdParams& p, int cg, int ew, cudaStream_t stream);
+// max_sms > 0: the persistent grid takes at most that many SMs (the rest is left to communication kernels)
+int launch_forward_tiles(const FwdParams& p, int cg, int ew, int max_sms, cudaStream_t stream);
 int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t stream);
-int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream);
+int launch_gemm(const GemmParams& p, int cg, int ew, int max_sms, cudaStream_t stream);
 // CTA pairs on 256 x wn tiles with one accumulator (MN-major B operands only); see gemm_wide_kernel
-int launch_gemm_wide(const GemmParams& p, int ew, cudaStream_t stream);
+int launch_gemm_wide(const GemmParams& p, int ew, int max_sms, cudaStream_t stream);
 int wide_stages(int wn);  // depth of the TMA ring that fits beside nothing else in shared memory
 int cta_group();   // SCLIP_CTA_GROUP environment override (1 or 2), default 2
 int epi_warps();   // SCLIP_EPI_WARPS environment override (8 or 16), default 16
-int max_sms();     // sclip_set_max_sms (0 = all)
+int sm_count();    // SMs of the current device
 int staging_slabs(int ew, bool split);  // 16 KiB G' staging slabs the backward tile kernel needs
 
-int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream);
+// t3_for_diag != null: also write this rank's positive-pair logits into diag_all (stash forward)
+int launch_prologue(const Workspace& w, const void* const x3[3], const float* t3_for_diag, cudaStream_t stream);
+int reduce_row_blocks(const sclip_problem& pb);  // entries per pair of rowterm_part
 int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream);
-int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream);
+// col_lse_all: the ranks' statistics gathered by a collective; peer_ws: read them from the peers' workspaces (and
+// compute the complete losses); both null: world == 1
+int launch_forward_loss(const Workspace& w, const float* col_lse_all, const void* const* peer_ws, float* loss3,
+                        cudaStream_t stream);
 int launch_backward_finish(const Workspace& w, const void* const x3[3], const float* t3, const float* g3,
                            const float* col_contrib, float grad_mult, void* const dx3[3], int out_f32, int stash,
                            float* dt3, cudaStream_t stream);
@@ -191,11 +212,9 @@ int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __
                      cudaStream_t stream);
 // peer-memory exchanges (world > 1, workspaces in symmetric memory); peer_ws[r] = base of rank r's workspace
 int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
-                       int block_threads, cudaStream_t stream);
+                       int block_threads, int epoch, cudaStream_t stream);
 int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, int block_threads,
                        cudaStream_t stream);
-int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t src_off, int count, float* out,
-                      bool sum_loss, cudaStream_t stream);
 int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream);
 
 }  // namespace sclip

@@ -2,6 +2,7 @@
 // construction and the stage launchers.  Host code only; the kernels live in sclip_tc.cu / sclip_simt.cu.
 #include <atomic>
 #include <cstdarg>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <cudaTypedefs.h>
@@ -31,9 +32,6 @@ int cta_group() {
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-static int g_max_sms = 0;
-int max_sms() { return g_max_sms; }
-
 int epi_warps() {
   static int cached = 0;
   if (cached == 0) {
@@ -51,8 +49,11 @@ int ring_stages(int slabs) {
   const int budget = 227 * 1024 - 14 * 1024 - 1024 - slabs * 16384;  // static smem + alignment slack
   int st = budget / stage_bytes;
   st = st > 6 ? 6 : (st < 2 ? 2 : st);
-  const char* e = getenv("SCLIP_STAGES");  // profiling experiments only
-  if (e != nullptr && atoi(e) >= 1 && atoi(e) < st) st = atoi(e);
+  static const int forced = [] {
+    const char* e = getenv("SCLIP_STAGES");  // profiling experiments only
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced >= 1 && forced < st) st = forced;
   return st;
 }
 
@@ -80,18 +81,15 @@ int wide_width(int n) {
 // cost of a unit: ring fill and epilogue, about 8 k-block times), keeping at least 32 k blocks per unit.  At most two:
 // the partial sums meet in a zeroed output through fp32 red.add, and 0 + a + b does not depend on the arrival order
 // (IEEE addition is commutative) whereas three or more addends would make the result run-to-run non-deterministic.
-int wide_ksplits(int tiles, int kb) {
-  int sms = 148;
-  {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      sms = n;
-  }
-  if (max_sms() > 0 && max_sms() < sms) sms = max_sms();
+int wide_ksplits(int tiles, int kb, int max_sms) {
+  int sms = sm_count();
+  if (max_sms > 0 && max_sms < sms) sms = max_sms;
   const int clusters = sms / 2 > 0 ? sms / 2 : 1;
-  const char* e = getenv("SCLIP_KSPLITS");  // profiling experiments only
-  if (e != nullptr && atoi(e) >= 1) return atoi(e) > kb ? kb : atoi(e);
+  static const int forced = [] {
+    const char* e = getenv("SCLIP_KSPLITS");  // profiling experiments only
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced >= 1) return forced > kb ? kb : forced;
   int best = 1;
   double best_cost = 0;
   for (int ks = 1; ks <= 2; ++ks) {
@@ -180,6 +178,8 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->fac_col = take(3 * 2 * align_up(bg, 64) * 4);
   lay->dot_part = take(3 * ((bl + 7) / 8) * 4);
   lay->status = take(4 * 4);
+  lay->rowterm_part = take(3 * static_cast<uint64_t>(reduce_row_blocks(*pb)) * 8);
+  lay->sync = take(kSyncWords * 4);
   lay->total_bytes = off;
   return SCLIP_OK;
 }
@@ -222,6 +222,8 @@ int resolve(const sclip_problem* pb, void* ws, Workspace* w) {
   w->fac_col = reinterpret_cast<float*>(b + l.fac_col);
   w->dot_part = reinterpret_cast<float*>(b + l.dot_part);
   w->status = reinterpret_cast<int*>(b + l.status);
+  w->rowterm_part = reinterpret_cast<double*>(b + l.rowterm_part);
+  w->sync = reinterpret_cast<int*>(b + l.sync);
   return SCLIP_OK;
 }
 
@@ -310,6 +312,54 @@ int encode_slot(const Workspace& w, int slot, CUtensorMap* out) {
   return SCLIP_ERR_ARGUMENT;
 }
 
+// Descriptors are cached per (workspace, problem): encoding one costs a driver call (~1-2 us) and a stage launch needs
+// 6 to 12 of them, which showed in the host time of the 8-GPU step (about 30 launches in 2.7 ms).  A small
+// most-recently-used table under a mutex; an entry is revalidated by comparing the whole key.
+struct MapCacheEntry {
+  const void* ws = nullptr;
+  int dev = -1;
+  sclip_problem pb{};
+  int cg = 0;
+  unsigned long long valid = 0;  // bit per slot
+  CUtensorMap maps[kNumSlots];
+  unsigned long long stamp = 0;
+};
+constexpr int kMapCacheEntries = 16;
+MapCacheEntry g_map_cache[kMapCacheEntries];
+unsigned long long g_map_clock = 0;
+std::mutex g_map_mutex;
+
+int cached_slot(const Workspace& w, int slot, CUtensorMap* out) {
+  int dev = 0;
+  SCLIP_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  MapCacheEntry* hit = nullptr;
+  MapCacheEntry* victim = &g_map_cache[0];
+  for (MapCacheEntry& e : g_map_cache) {
+    if (e.ws == w.base && e.dev == dev && e.cg == cta_group() && memcmp(&e.pb, &w.pb, sizeof(sclip_problem)) == 0) {
+      hit = &e;
+      break;
+    }
+    if (e.stamp < victim->stamp) victim = &e;
+  }
+  if (hit == nullptr) {
+    hit = victim;
+    hit->ws = w.base;
+    hit->dev = dev;
+    hit->pb = w.pb;
+    hit->cg = cta_group();
+    hit->valid = 0;
+  }
+  hit->stamp = ++g_map_clock;
+  if (!(hit->valid >> slot & 1ull)) {
+    const int rc = encode_slot(w, slot, &hit->maps[slot]);
+    if (rc) return rc;
+    hit->valid |= 1ull << slot;
+  }
+  *out = hit->maps[slot];
+  return SCLIP_OK;
+}
+
 // Collects the descriptors one kernel launch needs into the table carried by its parameters.
 struct MapTable {
   const Workspace& w;
@@ -328,7 +378,7 @@ struct MapTable {
       rc = SCLIP_ERR_ARGUMENT;
       return 0;
     }
-    const int r = encode_slot(w, slot, &dst[count]);
+    const int r = cached_slot(w, slot, &dst[count]);
     if (r) rc = r;
     local[slot] = count;
     return count++;
@@ -368,7 +418,7 @@ const char* sclip_last_error(void) { return g_error; }
 int sclip_plan(const sclip_problem* problem, sclip_layout* layout) { return plan(problem, layout); }
 
 int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
-                   void* stream) {
+                   const float* t3, int flags, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -378,19 +428,18 @@ int sclip_prologue(const sclip_problem* problem, void* ws, const void* img, cons
       set_error("embedding pointer %d must be non-null and 16-byte aligned", m);
       return SCLIP_ERR_ARGUMENT;
     }
+  const bool diag = (flags & SCLIP_PRO_DIAG) != 0;
+  if (diag && (t3 == nullptr || w.pb.math != SCLIP_MATH_F16)) {
+    set_error("SCLIP_PRO_DIAG needs t3 and a SCLIP_MATH_F16 problem");
+    return SCLIP_ERR_ARGUMENT;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SCLIP_CUDA_OK(cudaMemsetAsync(w.status, 0, 16, st));
-  return launch_prologue(w, x3, st);
-}
-
-int sclip_set_max_sms(int n) {
-  const int prev = g_max_sms;
-  g_max_sms = n < 0 ? 0 : n;
-  return prev;
+  return launch_prologue(w, x3, diag ? t3 : nullptr, st);
 }
 
 int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3, void* stream) {
-  return sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, 0, stream);
+  return sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, 0, 0, 0, stream);
 }
 
 int sclip_forward_diag(const sclip_problem* problem, void* ws, const float* t3, void* stream) {
@@ -416,13 +465,26 @@ int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3
 }
 
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
-                             int col_tile_begin, int col_tile_end, int flags, void* stream) {
+                             int col_tile_begin, int col_tile_end, int flags, int max_sms, int epoch, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
   if (t3 == nullptr) {
     set_error("t3 is null");
     return SCLIP_ERR_ARGUMENT;
+  }
+  const bool wait_peers = (flags & SCLIP_FWD_WAIT_PEERS) != 0;
+  if (wait_peers) {
+    const sclip_problem& q = w.pb;
+    if (q.world < 2 || q.world > SCLIP_MAX_PEERS || q.rows_local % 256 != 0 || q.rows_local * q.world != q.rows_global ||
+        q.row_offset % q.rows_local != 0 || max_sms < 0) {
+      set_error("SCLIP_FWD_WAIT_PEERS needs 2 <= world <= %d equal row shards that are multiples of 256", SCLIP_MAX_PEERS);
+      return SCLIP_ERR_ARGUMENT;
+    }
+    // one launch over every column, starting at this rank's own (the kernel wraps around)
+    col_tile_begin = q.row_offset / 256;
+    col_tile_end = col_tile_begin + w.lay.col_tiles;
+    flags |= SCLIP_FWD_WRAP;
   }
   const bool wrap = (flags & SCLIP_FWD_WRAP) != 0;
   if (!wrap && col_tile_end > w.lay.col_tiles) col_tile_end = w.lay.col_tiles;
@@ -462,7 +524,15 @@ int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float
   }
   p.stages = ring_stages(p.stash ? 4 : 0);
   p.acc_scale = w.pb.math == SCLIP_MATH_F16X3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
-  return launch_forward_tiles(p, cta_group(), epi_warps(), static_cast<cudaStream_t>(stream));
+  if (wait_peers) {
+    p.wait_peers = 1;
+    p.tiles_per_rank = w.pb.rows_local / 256;
+    p.world = w.pb.world;
+    p.rank = w.pb.row_offset / w.pb.rows_local;
+    p.landed = w.sync + kSyncLanded;
+    p.epoch = epoch;
+  }
+  return launch_forward_tiles(p, cta_group(), epi_warps(), max_sms, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_reduce(const sclip_problem* problem, void* ws, void* stream) {
@@ -476,7 +546,7 @@ int sclip_forward_loss(const sclip_problem* problem, void* ws, const float* col_
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
-  return launch_forward_loss(w, col_lse_all, loss3, static_cast<cudaStream_t>(stream));
+  return launch_forward_loss(w, col_lse_all, nullptr, loss3, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
@@ -519,7 +589,7 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
 }
 
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
-                              int flags, void* stream) {
+                              int max_sms, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -552,7 +622,7 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
     if (do_col) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
   }
   int nj = 0, tiles = 0;
-  (void)flags;  // reserved (round 1 used a bit for the in-GEMM stash conversion experiment, commit 5c56fe2)
+  if (max_sms < 0) max_sms = 0;
   auto add_role = [&](Job& job, int m, bool row_role) {
     if (row_role) {  // G'_{pair m} (rows_local x rows_global, K-major) . xhat_{col modality} (k = global row)
       const int pr = modality_row_pair(m), cm = pair_col_modality(pr);
@@ -615,7 +685,7 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
       kb_max = kb > kb_max ? kb : kb_max;
       base_tiles += job.m_tiles * job.n_tiles;
     }
-    const int ks = wide_ksplits(base_tiles, kb_max);
+    const int ks = wide_ksplits(base_tiles, kb_max, max_sms);
     tiles = 0;
     for (int j = 0; j < nj; ++j) {
       Job& job = p.jobs[j];
@@ -629,11 +699,11 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
     }
     p.total_tiles = tiles;
     p.stages = wide_stages(p.wn);
-    return launch_gemm_wide(p, epi_warps(), st);
+    return launch_gemm_wide(p, epi_warps(), max_sms, st);
   }
   p.total_tiles = tiles;
   p.stages = ring_stages(0);
-  return launch_gemm(p, cta_group(), epi_warps(), st);
+  return launch_gemm(p, cta_group(), epi_warps(), max_sms, st);
 }
 
 int sclip_backward_finish(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
@@ -727,7 +797,7 @@ int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, in
   p.alpha0 = x3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
   p.log_alpha = log_scale;
   p.stages = ring_stages(0);
-  return launch_gemm(p, cg, epi_warps(), st);
+  return launch_gemm(p, cg, epi_warps(), 0, st);
 }
 
 static int check_peers(const Workspace& w, void* ws, const void* const* peer_ws) {
@@ -759,7 +829,7 @@ static bool bad_block(int block_threads, int limit) {
 }
 
 int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
-                      int max_blocks, int block_threads, void* stream) {
+                      int max_blocks, int block_threads, int epoch, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (!rc) rc = check_peers(w, ws, peer_ws);
@@ -770,24 +840,11 @@ int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const*
   }
   if (bad_block(block_threads, 1024)) return SCLIP_ERR_ARGUMENT;
   if (count == 0) return SCLIP_OK;
-  return launch_pull_shards(w, peer_ws, first, count, max_blocks, block_threads, static_cast<cudaStream_t>(stream));
+  return launch_pull_shards(w, peer_ws, first, count, max_blocks, block_threads, epoch, static_cast<cudaStream_t>(stream));
 }
 
-int sclip_pull_col_lse(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* col_lse_all,
-                       void* stream) {
-  Workspace w;
-  int rc = resolve(problem, ws, &w);
-  if (!rc) rc = check_peers(w, ws, peer_ws);
-  if (rc) return rc;
-  if (col_lse_all == nullptr) {
-    set_error("col_lse_all is null");
-    return SCLIP_ERR_ARGUMENT;
-  }
-  return launch_pull_stats(w, peer_ws, w.lay.lse_col_local, 3 * w.pb.rows_global, col_lse_all, false,
-                           static_cast<cudaStream_t>(stream));
-}
-
-int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3, void* stream) {
+int sclip_forward_loss_peers(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3,
+                             void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (!rc) rc = check_peers(w, ws, peer_ws);
@@ -796,7 +853,21 @@ int sclip_pull_loss(const sclip_problem* problem, void* ws, const void* const* p
     set_error("loss3 is null");
     return SCLIP_ERR_ARGUMENT;
   }
-  return launch_pull_stats(w, peer_ws, w.lay.loss_part, 3, loss3, true, static_cast<cudaStream_t>(stream));
+  return launch_forward_loss(w, nullptr, peer_ws, loss3, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_read_status(const sclip_problem* problem, void* ws, int32_t* status_host, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (status_host == nullptr) {
+    set_error("status_host is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SCLIP_CUDA_OK(cudaMemcpyAsync(status_host, w.status, 16, cudaMemcpyDeviceToHost, st));
+  SCLIP_CUDA_OK(cudaStreamSynchronize(st));
+  return SCLIP_OK;
 }
 
 int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* const* peer_ws, int max_blocks,
@@ -813,8 +884,38 @@ int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* c
   return launch_pull_reduce(w, peer_ws, max_blocks, block_threads, static_cast<cudaStream_t>(stream));
 }
 
-// the single-GPU convenience calls remember, per workspace, whether the last forward stashed
-static thread_local const void* g_stashed_ws = nullptr;
+// The single-GPU convenience calls remember, per workspace, what the last forward left for the backward:
+// 0 nothing (forward only, or consumed), 1 statistics only (the backward recomputes the similarities), 2 a stash.
+namespace {
+struct KeptState {
+  const void* ws;
+  int state;
+};
+constexpr int kKeptEntries = 32;
+KeptState g_kept[kKeptEntries];
+std::mutex g_kept_mutex;
+
+void set_kept(const void* ws, int state) {
+  std::lock_guard<std::mutex> lock(g_kept_mutex);
+  KeptState* slot = nullptr;
+  for (KeptState& k : g_kept) {
+    if (k.ws == ws) {
+      slot = &k;
+      break;
+    }
+    if (slot == nullptr && (k.ws == nullptr || k.state == 0)) slot = &k;
+  }
+  if (slot == nullptr) slot = &g_kept[0];
+  slot->ws = ws;
+  slot->state = state;
+}
+int get_kept(const void* ws) {
+  std::lock_guard<std::mutex> lock(g_kept_mutex);
+  for (const KeptState& k : g_kept)
+    if (k.ws == ws) return k.state;
+  return 0;
+}
+}  // namespace
 
 int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const void* txt, const void* aud,
                   const float* t3, int keep_for_backward, float* loss3, void* stream) {
@@ -822,13 +923,18 @@ int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const
     set_error("sclip_forward is the single-GPU entry point (world must be 1); use the stage calls when sharded");
     return SCLIP_ERR_ARGUMENT;
   }
-  const bool stash = keep_for_backward && problem != nullptr && problem->math == SCLIP_MATH_F16;
-  int rc = sclip_prologue(problem, ws, img, txt, aud, stream);
-  if (!rc && stash) rc = sclip_forward_diag(problem, ws, t3, stream);
-  if (!rc) rc = sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, stash ? SCLIP_FWD_STASH : 0, stream);
+  if (t3 == nullptr) {
+    set_error("t3 is null");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  // stash when a backward follows, the operands are fp16 and the row is long enough that 4 bytes of HBM traffic per
+  // logit beat 2 dim flop of recomputation (measured crossover on B200 between dim 512 and 768)
+  const bool stash = keep_for_backward && problem != nullptr && problem->math == SCLIP_MATH_F16 && problem->dim >= 640;
+  int rc = sclip_prologue(problem, ws, img, txt, aud, t3, stash ? SCLIP_PRO_DIAG : 0, stream);
+  if (!rc) rc = sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, stash ? SCLIP_FWD_STASH : 0, 0, 0, stream);
   if (!rc) rc = sclip_forward_reduce(problem, ws, stream);
   if (!rc) rc = sclip_forward_loss(problem, ws, nullptr, loss3, stream);
-  if (!rc) g_stashed_ws = stash ? ws : (g_stashed_ws == ws ? nullptr : g_stashed_ws);
+  if (ws != nullptr) set_kept(ws, rc ? 0 : (stash ? 2 : (keep_for_backward ? 1 : 0)));
   return rc;
 }
 
@@ -839,9 +945,15 @@ int sclip_backward(const sclip_problem* problem, void* ws, const void* img, cons
     set_error("sclip_backward is the single-GPU entry point (world must be 1); use the stage calls when sharded");
     return SCLIP_ERR_ARGUMENT;
   }
-  const bool stashed = ws != nullptr && g_stashed_ws == ws;
+  const int kept = ws != nullptr ? get_kept(ws) : 0;
+  if (kept == 0) {
+    set_error("sclip_backward needs a preceding sclip_forward(keep_for_backward = 1) on this workspace; a forward "
+              "serves one backward (its stashed tiles are converted in place)");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const bool stashed = kept == 2;
+  set_kept(ws, 0);
   int rc = stashed ? sclip_backward_scale(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
-  if (stashed) g_stashed_ws = nullptr;  // converted in place: this stash serves one backward
   if (!rc) rc = sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, stream);
   if (!rc)
     rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32,
@@ -878,7 +990,7 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
   if (wide_enabled() && b_mn && n > 256) {
     p.wn = wide_width(n);
     p.jobs[0].n_tiles = ceil_div(n, p.wn);
-    const int ks = wide_ksplits(p.jobs[0].m_tiles * p.jobs[0].n_tiles, ceil_div(k, BK));
+    const int ks = wide_ksplits(p.jobs[0].m_tiles * p.jobs[0].n_tiles, ceil_div(k, BK), 0);
     p.jobs[0].ksplits = ks;
     if (ks > 1) {
       if (ldc != n) {
@@ -889,11 +1001,11 @@ int sclip_gemm_f16(const void* a, int64_t lda, int a_mn, const void* b, int64_t 
     }
     p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles * ks;
     p.stages = wide_stages(p.wn);
-    return launch_gemm_wide(p, epi_warps(), st);
+    return launch_gemm_wide(p, epi_warps(), 0, st);
   }
   p.total_tiles = p.jobs[0].m_tiles * p.jobs[0].n_tiles;
   p.stages = ring_stages(0);
-  return launch_gemm(p, cta_group(), epi_warps(), st);
+  return launch_gemm(p, cta_group(), epi_warps(), 0, st);
 }
 
 }  // extern "C"

@@ -122,116 +122,268 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) prologue_kernel(const Prol
   }
 }
 
+// All three modalities of one row per warp, and -- when a stash forward follows -- the positive-pair logits
+// diag_all[p][row_offset + i] = s_p <xr_i, xc_i> of the fp16 operands as the tensor cores will see them.
+struct Prologue3Args {
+  const void* x[3];
+  __half* hi[3];
+  __half* lo[3];
+  float* inv_norm;
+  const float* t3;    // null: no positive-pair logits
+  float* diag_all;    // [3][rows_global]
+  int rows, dim, rows_global;
+  int row_offset;
+  float opscale;
+  int split;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kRowsPerBlock * 32) prologue3_kernel(const Prologue3Args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kRowsPerBlock + warp;
+  if (row >= a.rows) return;
+  const T* xr[3];
+  float ss[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int m = 0; m < 3; ++m) xr[m] = static_cast<const T*>(a.x[m]) + static_cast<size_t>(row) * a.dim;
+  for (int i = lane * 8; i < a.dim; i += 256) {
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      float v[8];
+      load8(xr[m] + i, v);
+      float part = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part = fmaf(v[k], v[k], part);
+      ss[m] += part;
+    }
+  }
+  float nrm[3];
+#pragma unroll
+  for (int m = 0; m < 3; ++m) {
+    nrm[m] = sqrtf(warp_sum_f(ss[m]));
+    if (lane == 0) a.inv_norm[static_cast<size_t>(m) * a.rows + row] = 1.0f / nrm[m];
+  }
+  float dots[3] = {0.f, 0.f, 0.f};
+  const size_t out_off = static_cast<size_t>(a.row_offset + row) * a.dim;
+  for (int i = lane * 8; i < a.dim; i += 256) {
+    float r[3][8];  // operands rounded to fp16, as the tensor cores see them
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      float v[8];
+      load8(xr[m] + i, v);  // second read hits L1/L2
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (v[k] / nrm[m]) * a.opscale;
+      const uint4 packed = pack8_half(v);
+      *reinterpret_cast<uint4*>(a.hi[m] + out_off + i) = packed;
+      const __half2* h = reinterpret_cast<const __half2*>(&packed);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        r[m][2 * k] = f.x;
+        r[m][2 * k + 1] = f.y;
+      }
+      if (a.split) {
+        float l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = v[k] - r[m][k];
+        *reinterpret_cast<uint4*>(a.lo[m] + out_off + i) = pack8_half(l);
+      }
+    }
+    if (a.t3 != nullptr) {
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {
+        float part = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) part = fmaf(r[p][k], r[(p + 1) % 3][k], part);
+        dots[p] += part;
+      }
+    }
+  }
+  if (a.t3 != nullptr) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+      const float d = warp_sum_f(dots[p]);
+      if (lane == 0) a.diag_all[static_cast<size_t>(p) * a.rows_global + a.row_offset + row] = expf(a.t3[p]) * d;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward reduce
+// Merge of the per-tile statistics: lse_row / row_inv of this rank's rows, lse_col_local / col_sum_local over this
+// rank's rows, and per-block partial sums of the row term of the loss.  A block handles 64 rows (or columns); its
+// 256 threads split the tiles to merge four ways so that enough loads are in flight (the round-1 kernel, one thread
+// per row walking all tiles, ran at 1.7 TB/s), and the four partial sums are combined in a fixed order.
 struct ReduceArgs {
   const float* row_part;
   const float* col_part;
   const float* tile_ref;
+  const float* diag;
   float* lse_row;
   float* lse_col_local;
   float* row_inv;
   float* col_sum_local;
+  double* rowterm_part;  // [3][row_blocks]: sum over the block's rows of (lse_row_i - 2 L_ii)
   int* status;
   int rows_local, rows_global;
   int nti;       // layout stride (128-row tiles, padded)
   int nti_done;  // 128-row tiles the forward kernel actually produced
   int ntj;
+  int row_blocks, col_blocks;
 };
 
+constexpr int kReduceRows = 64;
+
 __global__ void __launch_bounds__(256) forward_reduce_kernel(const ReduceArgs a) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  __shared__ float part_sum[4][kReduceRows];
+  __shared__ double term[kReduceRows];
+  const int r = threadIdx.x & (kReduceRows - 1);
+  const int part = threadIdx.x / kReduceRows;  // 0..3
   const int p = blockIdx.y;
+  const bool row_side = static_cast<int>(blockIdx.x) < a.row_blocks;
   bool bad = false;
-  if (i < a.rows_local) {
-    const int ti = i / BM;
+  if (row_side) {
+    const int i = blockIdx.x * kReduceRows + r;
+    const bool ok = i < a.rows_local;
+    const int ii = ok ? i : a.rows_local - 1;
+    const int ti = ii / BM;
     const float* ref = a.tile_ref + (static_cast<size_t>(p) * a.nti + ti) * a.ntj;
     float R = -INFINITY;
     for (int tj = 0; tj < a.ntj; ++tj) R = fmaxf(R, __ldg(ref + tj));
-    // four independent partial sums keep the (coalesced) loads of several column tiles in flight
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    const float* rp0 = a.row_part + static_cast<size_t>(p) * a.ntj * 2 * a.rows_local + i;
+    const float* rp0 = a.row_part + static_cast<size_t>(p) * a.ntj * 2 * a.rows_local + ii;
     const size_t pitch = static_cast<size_t>(2) * a.rows_local;  // two slots per column tile (one per 128-column slice)
-    auto term = [&](int tj) {
+    auto term_of = [&](int tj) {
       const float* rp = rp0 + tj * pitch;
       return (__ldg(rp) + __ldg(rp + a.rows_local)) * __expf(__ldg(ref + tj) - R);
     };
-    int tj = 0;
-    for (; tj + 3 < a.ntj; tj += 4) {
-      const float t0 = term(tj), t1 = term(tj + 1), t2 = term(tj + 2), t3 = term(tj + 3);
+    const int per = (a.ntj + 3) / 4, lo = part * per, hi = min(a.ntj, lo + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int tj = lo;
+    for (; tj + 3 < hi; tj += 4) {
+      const float t0 = term_of(tj), t1 = term_of(tj + 1), t2 = term_of(tj + 2), t3 = term_of(tj + 3);
       s0 += t0; s1 += t1; s2 += t2; s3 += t3;
     }
-    for (; tj < a.ntj; ++tj) s0 += term(tj);
-    const float sum = (s0 + s1) + (s2 + s3);
-    const float lse = R + logf(sum);
-    a.lse_row[static_cast<size_t>(p) * a.rows_local + i] = lse;
-    a.row_inv[static_cast<size_t>(p) * a.rows_local + i] = 1.0f / sum;  // meaningful when every tile reference is 0
-    bad |= !isfinite(lse);
-  }
-  if (i < a.rows_global) {
-    const int tj = i / BN;
+    for (; tj < hi; ++tj) s0 += term_of(tj);
+    part_sum[part][r] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (part == 0) {
+      const float sum = (part_sum[0][r] + part_sum[1][r]) + (part_sum[2][r] + part_sum[3][r]);
+      const float lse = R + logf(sum);
+      double t = 0.0;
+      if (ok) {
+        a.lse_row[static_cast<size_t>(p) * a.rows_local + i] = lse;
+        a.row_inv[static_cast<size_t>(p) * a.rows_local + i] = 1.0f / sum;  // meaningful when every tile reference is 0
+        bad |= !isfinite(lse);
+        t = static_cast<double>(lse) - 2.0 * static_cast<double>(a.diag[static_cast<size_t>(p) * a.rows_local + i]);
+      }
+      term[r] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double acc = 0.0;
+      for (int k = 0; k < kReduceRows; ++k) acc += term[k];
+      a.rowterm_part[static_cast<size_t>(p) * a.row_blocks + blockIdx.x] = acc;
+    }
+  } else {
+    const int j = (blockIdx.x - a.row_blocks) * kReduceRows + r;
+    const bool ok = j < a.rows_global;
+    const int jj = ok ? j : a.rows_global - 1;
+    const int tj = jj / BN;
     float R = -INFINITY;
-    for (int ti = 0; ti < a.nti_done; ++ti) R = fmaxf(R, a.tile_ref[(static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj]);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    auto term = [&](int ti) {
-      return __ldg(a.col_part + (static_cast<size_t>(p) * a.nti + ti) * a.rows_global + i) *
+    for (int ti = 0; ti < a.nti_done; ++ti) R = fmaxf(R, __ldg(a.tile_ref + (static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj));
+    auto term_of = [&](int ti) {
+      return __ldg(a.col_part + (static_cast<size_t>(p) * a.nti + ti) * a.rows_global + jj) *
              __expf(__ldg(a.tile_ref + (static_cast<size_t>(p) * a.nti + ti) * a.ntj + tj) - R);
     };
-    int ti = 0;
-    for (; ti + 3 < a.nti_done; ti += 4) {
-      const float t0 = term(ti), t1 = term(ti + 1), t2 = term(ti + 2), t3 = term(ti + 3);
+    const int per = (a.nti_done + 3) / 4, lo = part * per, hi = min(a.nti_done, lo + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int ti = lo;
+    for (; ti + 3 < hi; ti += 4) {
+      const float t0 = term_of(ti), t1 = term_of(ti + 1), t2 = term_of(ti + 2), t3 = term_of(ti + 3);
       s0 += t0; s1 += t1; s2 += t2; s3 += t3;
     }
-    for (; ti < a.nti_done; ++ti) s0 += term(ti);
-    const float sum = (s0 + s1) + (s2 + s3);
-    const float lse = R + logf(sum);
-    a.lse_col_local[static_cast<size_t>(p) * a.rows_global + i] = lse;
-    a.col_sum_local[static_cast<size_t>(p) * a.rows_global + i] = sum;
-    bad |= !isfinite(lse);
+    for (; ti < hi; ++ti) s0 += term_of(ti);
+    part_sum[part][r] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (part == 0 && ok) {
+      const float sum = (part_sum[0][r] + part_sum[1][r]) + (part_sum[2][r] + part_sum[3][r]);
+      const float lse = R + logf(sum);
+      a.lse_col_local[static_cast<size_t>(p) * a.rows_global + j] = lse;
+      a.col_sum_local[static_cast<size_t>(p) * a.rows_global + j] = sum;
+      bad |= !isfinite(lse);
+    }
   }
   if (bad) atomicOr(a.status, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ forward loss
+// lse_col = log-sum-exp over the ranks' column statistics, the normalisers of the backward, and the losses.
+//   share mode (world == 1, or the statistics of the other ranks came through a collective into `col_lse_all`):
+//     loss3[p] = this rank's share ( sum_i (lse_row_i - L_ii) + sum_i (lse_col_{off+i} - L_ii) ) / (2 B);
+//     summed over ranks it is clip_loss.
+//   peer mode (`peer` = every rank's workspace, mapped): the column statistics and the row terms of all ranks are read
+//     straight from their workspaces, and every rank computes the complete losses
+//     loss3[p] = ( sum_r rowterm_r + sum_j lse_col_j ) / (2 B)   -- same data, same order, same result on every rank.
 struct LossArgs {
-  const float* lse_row;
   const float* lse_col_local;
   const float* col_lse_all;  // [world][3][rows_global] or null
-  const float* diag;
+  const uint8_t* peer[SCLIP_MAX_PEERS];  // peer mode: workspace bases in rank order (peer[0] == null: share mode)
+  unsigned long long lse_col_local_off, rowterm_off;
+  const double* rowterm_part;
   const float* col_sum_local;
   float* lse_col;
   float* col_inv;
   float* loss_part;
   float* loss3;
-  int rows_local, rows_global, row_offset, world;
+  int rows_local, rows_global, row_offset, world, row_blocks;
 };
+
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {  // peer data: L2 only, never a stale L1 line
+  return __ldcg(p);
+}
 
 __global__ void __launch_bounds__(1024) forward_loss_kernel(const LossArgs a) {
   __shared__ double red[32];
   const int p = blockIdx.x;
+  const bool peers = a.peer[0] != nullptr;
   float* lse_col = a.lse_col + static_cast<size_t>(p) * a.rows_global;
+  double acc = 0.0;
   for (int j = threadIdx.x; j < a.rows_global; j += blockDim.x) {
     float v;
-    if (a.col_lse_all == nullptr) {
+    if (!peers && a.col_lse_all == nullptr) {
       v = a.lse_col_local[static_cast<size_t>(p) * a.rows_global + j];
       a.col_inv[static_cast<size_t>(p) * a.rows_global + j] = 1.0f / a.col_sum_local[static_cast<size_t>(p) * a.rows_global + j];
     } else {
+      float x[SCLIP_MAX_PEERS];
       float mx = -INFINITY;
-      for (int w = 0; w < a.world; ++w)
-        mx = fmaxf(mx, a.col_lse_all[(static_cast<size_t>(w) * 3 + p) * a.rows_global + j]);
+#pragma unroll
+      for (int w = 0; w < SCLIP_MAX_PEERS; ++w) {
+        if (w < a.world) {
+          x[w] = peers ? ld_relaxed_sys(reinterpret_cast<const float*>(a.peer[w] + a.lse_col_local_off) +
+                                        static_cast<size_t>(p) * a.rows_global + j)
+                       : a.col_lse_all[(static_cast<size_t>(w) * 3 + p) * a.rows_global + j];
+          mx = fmaxf(mx, x[w]);
+        }
+      }
       float sum = 0.f;
-      for (int w = 0; w < a.world; ++w)
-        sum += expf(a.col_lse_all[(static_cast<size_t>(w) * 3 + p) * a.rows_global + j] - mx);
+#pragma unroll
+      for (int w = 0; w < SCLIP_MAX_PEERS; ++w)
+        if (w < a.world) sum += expf(x[w] - mx);
       v = mx + logf(sum);
       a.col_inv[static_cast<size_t>(p) * a.rows_global + j] = expf(-v);
     }
     lse_col[j] = v;
+    // column term: every column in peer mode, the columns of this rank's own rows otherwise
+    if (peers || (j >= a.row_offset && j < a.row_offset + a.rows_local)) acc += static_cast<double>(v);
   }
-  __syncthreads();
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < a.rows_local; i += blockDim.x) {
-    const double d = a.diag[static_cast<size_t>(p) * a.rows_local + i];
-    acc += (static_cast<double>(a.lse_row[static_cast<size_t>(p) * a.rows_local + i]) - d) +
-           (static_cast<double>(lse_col[a.row_offset + i]) - d);
+  // row term: sum_i (lse_row_i - 2 L_ii) from the per-block partial sums of forward_reduce_kernel
+  if (peers) {
+    for (int w = 0; w < a.world; ++w) {
+      const double* rt = reinterpret_cast<const double*>(a.peer[w] + a.rowterm_off) + static_cast<size_t>(p) * a.row_blocks;
+      for (int i = threadIdx.x; i < a.row_blocks; i += blockDim.x) acc += __ldcg(rt + i);
+    }
+  } else {
+    for (int i = threadIdx.x; i < a.row_blocks; i += blockDim.x)
+      acc += a.rowterm_part[static_cast<size_t>(p) * a.row_blocks + i];
   }
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -258,7 +410,11 @@ struct FinishArgs {
   const float* t3;
   const float* g3;
   float* dot_part;           // [3][gridDim.x] per-block sums of <xhat, dxhat_total> (stash mode: dlogit_scale)
+  const float* dt_part;      // recompute mode: [3][ntiles] tile sums of G' cos
+  float* dt3;                // dlogit_scale out (null: not wanted)
+  unsigned int* done;        // block counter (zero between launches): the last block to finish reduces dlogit_scale
   int rows, dim, rows_global;
+  int ntiles;
   int stash;
   float grad_mult;
 };
@@ -317,38 +473,34 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) backward_finish_kernel(con
       a.dot_part[static_cast<size_t>(m) * gridDim.x + blockIdx.x] = sum;
     }
   }
-}
-
-struct DtArgs {
-  const float* dt_part;   // recompute mode: [3][ntiles] tile sums of G' cos
-  const float* dot_part;  // stash mode: [3][nblocks] block sums of <xhat_m, dxhat_total_m>
-  const float* t3;
-  const float* g3;
-  float* dt3;
-  int ntiles;
-  int nblocks;
-  int rows_global;
-  int stash;
-  float grad_mult;
-};
-
-__global__ void __launch_bounds__(1024) dt_finish_kernel(const DtArgs a) {
-  __shared__ double red[32];
+  if (a.dt3 == nullptr) return;
+  // dlogit_scale: the last block to arrive sums the partials (fixed order: deterministic) -- no second launch
+  __shared__ bool last;
+  __shared__ double red[kRowsPerBlock];
   __shared__ double total[3];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int n = gridDim.x * gridDim.y;
+    last = atomicAdd(a.done, 1u) == n - 1;
+    if (last) *a.done = 0u;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const int count = a.stash ? static_cast<int>(gridDim.x) : a.ntiles;
+  const float* src = a.stash ? a.dot_part : a.dt_part;
   for (int p = 0; p < 3; ++p) {
     double acc = 0.0;
-    if (a.stash) {
-      for (int i = threadIdx.x; i < a.nblocks; i += blockDim.x) acc += a.dot_part[static_cast<size_t>(p) * a.nblocks + i];
-    } else {
-      for (int i = threadIdx.x; i < a.ntiles; i += blockDim.x) acc += a.dt_part[static_cast<size_t>(p) * a.ntiles + i];
-    }
+    for (int i = threadIdx.x; i < count; i += blockDim.x) acc += __ldcg(src + static_cast<size_t>(p) * count + i);
     acc = warp_sum_d(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    if (lane == 0) red[warp] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-      double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
-      v = warp_sum_d(v);
-      if (threadIdx.x == 0) total[p] = v;
+    if (threadIdx.x == 0) {
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRowsPerBlock; ++w) v += red[w];
+      total[p] = v;
     }
     __syncthreads();
   }
@@ -509,47 +661,65 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
 __device__ __forceinline__ uint4 ld_peer(const uint4* p) { return __ldcg(p); }  // L2 only: never a stale L1 line
 
 struct PullShardArgs {
-  const uint8_t* peer[SCLIP_MAX_PEERS];   // workspace bases of the selected source ranks
+  const uint8_t* peer[SCLIP_MAX_PEERS];   // workspace bases of the selected source ranks, in pull order
   int peer_rank[SCLIP_MAX_PEERS];
+  int count;
   uint8_t* local;
   unsigned long long xhat_off, xhat_lo_off, diag_off;
   int nseg;  // 3, or 6 with the low halves
   int rows_local, rows_global, dim;
+  int* landed;            // [SCLIP_MAX_PEERS] per source rank: epoch of the last shard that is complete in this workspace
+  unsigned int* arrived;  // [SCLIP_MAX_PEERS] block counters (zero between launches)
+  int epoch;
 };
 
+// Every block walks the source ranks in the same order and copies its slice of each shard, so the shards complete one
+// after the other (the tile kernel consumes them in that order).  The last block to finish a shard publishes
+// landed[rank] = epoch with release semantics; forward tiles launched with SCLIP_FWD_WAIT_PEERS acquire it.
 __global__ void __launch_bounds__(1024) pull_shards_kernel(const PullShardArgs a) {
-  const int pi = blockIdx.y;
-  const uint8_t* src = a.peer[pi];
-  const size_t row0 = static_cast<size_t>(a.peer_rank[pi]) * a.rows_local;
   const size_t seg_units = static_cast<size_t>(a.rows_local) * a.dim * 2 / 16;  // 16-byte units per modality shard
   const size_t total = a.nseg * seg_units;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  auto locate = [&](size_t u) {
-    const int sg = static_cast<int>(u / seg_units);
-    const size_t w = u - sg * seg_units;
-    return (sg < 3 ? a.xhat_off : a.xhat_lo_off) + ((static_cast<size_t>(sg % 3) * a.rows_global + row0) * a.dim) * 2 +
-           w * 16;
-  };
-  size_t u = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  for (; u + 3 * stride < total; u += 4 * stride) {  // four independent 16-byte loads in flight per thread
-    size_t o[4];
-    uint4 v[4];
+  for (int pi = 0; pi < a.count; ++pi) {
+    const uint8_t* src = a.peer[pi];
+    const size_t row0 = static_cast<size_t>(a.peer_rank[pi]) * a.rows_local;
+    auto locate = [&](size_t u) {
+      const int sg = static_cast<int>(u / seg_units);
+      const size_t w = u - sg * seg_units;
+      return (sg < 3 ? a.xhat_off : a.xhat_lo_off) + ((static_cast<size_t>(sg % 3) * a.rows_global + row0) * a.dim) * 2 +
+             w * 16;
+    };
+    size_t u = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; u + 3 * stride < total; u += 4 * stride) {  // four independent 16-byte loads in flight per thread
+      size_t o[4];
+      uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) o[k] = locate(u + k * stride);
+      for (int k = 0; k < 4; ++k) o[k] = locate(u + k * stride);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = ld_peer(reinterpret_cast<const uint4*>(src + o[k]));
+      for (int k = 0; k < 4; ++k) v[k] = ld_peer(reinterpret_cast<const uint4*>(src + o[k]));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(a.local + o[k]) = v[k];
-  }
-  for (; u < total; u += stride) {
-    const size_t o = locate(u);
-    *reinterpret_cast<uint4*>(a.local + o) = ld_peer(reinterpret_cast<const uint4*>(src + o));
-  }
-  // positive-pair logits of the peer's rows (stash scaling)
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3u * a.rows_local; i += stride) {
-    const size_t p = i / a.rows_local, r = i - p * a.rows_local;
-    const size_t o = a.diag_off + (p * a.rows_global + row0 + r) * 4;
-    *reinterpret_cast<float*>(a.local + o) = __ldcg(reinterpret_cast<const float*>(src + o));
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(a.local + o[k]) = v[k];
+    }
+    for (; u < total; u += stride) {
+      const size_t o = locate(u);
+      *reinterpret_cast<uint4*>(a.local + o) = ld_peer(reinterpret_cast<const uint4*>(src + o));
+    }
+    // positive-pair logits of the peer's rows (stash scaling)
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3u * a.rows_local; i += stride) {
+      const size_t p = i / a.rows_local, r = i - p * a.rows_local;
+      const size_t o = a.diag_off + (p * a.rows_global + row0 + r) * 4;
+      *reinterpret_cast<float*>(a.local + o) = __ldcg(reinterpret_cast<const float*>(src + o));
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int r = a.peer_rank[pi];
+      if (atomicAdd(&a.arrived[r], 1u) == gridDim.x - 1) {
+        a.arrived[r] = 0u;
+        __threadfence();
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.landed + r), "r"(a.epoch) : "memory");
+      }
+    }
   }
 }
 
@@ -596,50 +766,29 @@ __global__ void __launch_bounds__(512) pull_reduce_kernel(const PullReduceArgs a
   }
 }
 
-struct PullStatsArgs {
-  const uint8_t* peer[SCLIP_MAX_PEERS];  // all ranks in rank order
-  int world;
-  unsigned long long src_off;  // float array at this offset of every workspace
-  float* out;                  // [world][count]
-  int count;
-};
-
-__global__ void __launch_bounds__(256) pull_stats_kernel(const PullStatsArgs a) {
-  const int r = blockIdx.y;
-  const float* src = reinterpret_cast<const float*>(a.peer[r] + a.src_off);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.count; i += gridDim.x * blockDim.x)
-    a.out[static_cast<size_t>(r) * a.count + i] = __ldcg(src + i);
-}
-
-// loss3[p] = sum over ranks of loss_part_r[p]
-__global__ void pull_loss_kernel(const PullStatsArgs a) {
-  if (threadIdx.x < 3) {
-    float s = 0.f;
-    for (int r = 0; r < a.world; ++r) s += __ldcg(reinterpret_cast<const float*>(a.peer[r] + a.src_off) + threadIdx.x);
-    a.out[threadIdx.x] = s;
-  }
-}
-
 }  // namespace
 
-int launch_prologue(const Workspace& w, const void* const x3[3], cudaStream_t stream) {
-  PrologueArgs a;
+int launch_prologue(const Workspace& w, const void* const x3[3], const float* t3_for_diag, cudaStream_t stream) {
+  Prologue3Args a;
   for (int m = 0; m < 3; ++m) {
     a.x[m] = x3[m];
     a.hi[m] = w.xhat[m];
     a.lo[m] = w.xhat_lo[m];
   }
   a.inv_norm = w.inv_norm;
+  a.t3 = t3_for_diag;
+  a.diag_all = w.diag_all;
   a.rows = w.pb.rows_local;
   a.dim = w.pb.dim;
+  a.rows_global = w.pb.rows_global;
   a.row_offset = w.pb.row_offset;
   a.split = w.pb.math == SCLIP_MATH_F16X3;
   a.opscale = a.split ? kOperandScaleX3 : 1.0f;
-  dim3 grid((a.rows + kRowsPerBlock - 1) / kRowsPerBlock, 3);
+  const int grid = (a.rows + kRowsPerBlock - 1) / kRowsPerBlock;
   if (w.pb.dtype == SCLIP_F32)
-    prologue_kernel<float><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
+    prologue3_kernel<float><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
   else
-    prologue_kernel<__nv_bfloat16><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
+    prologue3_kernel<__nv_bfloat16><<<grid, kRowsPerBlock * 32, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
@@ -666,19 +815,39 @@ int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __
   return SCLIP_OK;
 }
 
+int reduce_row_blocks(const sclip_problem& pb) { return (pb.rows_local + kReduceRows - 1) / kReduceRows; }
+
 int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream) {
-  ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.lse_row, w.lse_col_local, w.row_inv, w.col_sum_local, w.status,
-               w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, row_tiles_done, w.lay.col_tiles};
-  const int n = w.pb.rows_local > w.pb.rows_global ? w.pb.rows_local : w.pb.rows_global;
-  dim3 grid((n + 255) / 256, 3);
-  forward_reduce_kernel<<<grid, 256, 0, stream>>>(a);
+  const int rb = reduce_row_blocks(w.pb), cb = (w.pb.rows_global + kReduceRows - 1) / kReduceRows;
+  ReduceArgs a{w.row_part, w.col_part, w.tile_ref, w.diag, w.lse_row, w.lse_col_local, w.row_inv, w.col_sum_local,
+               w.rowterm_part, w.status, w.pb.rows_local, w.pb.rows_global, w.lay.row_tiles, row_tiles_done,
+               w.lay.col_tiles, rb, cb};
+  forward_reduce_kernel<<<dim3(rb + cb, 3), 256, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
 
-int launch_forward_loss(const Workspace& w, const float* col_lse_all, float* loss3, cudaStream_t stream) {
-  LossArgs a{w.lse_row, w.lse_col_local, col_lse_all, w.diag, w.col_sum_local, w.lse_col, w.col_inv, w.loss_part, loss3,
-             w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, w.pb.world};
+int launch_forward_loss(const Workspace& w, const float* col_lse_all, const void* const* peer_ws, float* loss3,
+                        cudaStream_t stream) {
+  LossArgs a;
+  memset(&a, 0, sizeof(a));
+  a.lse_col_local = w.lse_col_local;
+  a.col_lse_all = col_lse_all;
+  if (peer_ws != nullptr)
+    for (int r = 0; r < w.pb.world; ++r) a.peer[r] = static_cast<const uint8_t*>(peer_ws[r]);
+  a.lse_col_local_off = w.lay.lse_col_local;
+  a.rowterm_off = w.lay.rowterm_part;
+  a.rowterm_part = w.rowterm_part;
+  a.col_sum_local = w.col_sum_local;
+  a.lse_col = w.lse_col;
+  a.col_inv = w.col_inv;
+  a.loss_part = w.loss_part;
+  a.loss3 = loss3;
+  a.rows_local = w.pb.rows_local;
+  a.rows_global = w.pb.rows_global;
+  a.row_offset = w.pb.row_offset;
+  a.world = w.pb.world;
+  a.row_blocks = reduce_row_blocks(w.pb);
   forward_loss_kernel<<<3, 1024, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
@@ -706,6 +875,10 @@ int launch_backward_finish(const Workspace& w, const void* const x3[3], const fl
   a.grad_mult = grad_mult;
   dim3 grid((a.rows + kRowsPerBlock - 1) / kRowsPerBlock, 3);
   a.dot_part = stash ? w.dot_part : nullptr;
+  a.dt_part = w.dt_part;
+  a.dt3 = dt3;
+  a.done = reinterpret_cast<unsigned int*>(w.sync) + kSyncFinishDone;
+  a.ntiles = w.lay.row_tiles * w.lay.col_tiles;
   const int threads = kRowsPerBlock * 32;
   if (w.pb.dtype == SCLIP_F32)
     backward_finish_kernel<float, float><<<grid, threads, 0, stream>>>(a);
@@ -714,12 +887,6 @@ int launch_backward_finish(const Workspace& w, const void* const x3[3], const fl
   else
     backward_finish_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, threads, 0, stream>>>(a);
   SCLIP_LAUNCHED();
-  if (dt3 != nullptr) {
-    DtArgs dd{w.dt_part, w.dot_part, t3, g3, dt3, w.lay.row_tiles * w.lay.col_tiles, static_cast<int>(grid.x),
-              w.pb.rows_global, stash, grad_mult};
-    dt_finish_kernel<<<1, 1024, 0, stream>>>(dd);
-    SCLIP_LAUNCHED();
-  }
   return SCLIP_OK;
 }
 
@@ -757,7 +924,7 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
 namespace sclip {
 
 int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
-                       int block_threads, cudaStream_t stream) {
+                       int block_threads, int epoch, cudaStream_t stream) {
   PullShardArgs a;
   memset(&a, 0, sizeof(a));
   const int world = w.pb.world, rank = w.pb.row_offset / w.pb.rows_local;
@@ -766,6 +933,7 @@ int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first
     a.peer[i] = static_cast<const uint8_t*>(peer_ws[r]);
     a.peer_rank[i] = r;
   }
+  a.count = count;
   a.local = w.base;
   a.xhat_off = w.lay.xhat;
   a.xhat_lo_off = w.lay.xhat_lo;
@@ -774,9 +942,11 @@ int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first
   a.rows_local = w.pb.rows_local;
   a.rows_global = w.pb.rows_global;
   a.dim = w.pb.dim;
-  int bx = max_blocks / count;
-  if (bx < 1) bx = 1;
-  pull_shards_kernel<<<dim3(bx, count), block_threads, 0, stream>>>(a);
+  a.landed = w.sync + kSyncLanded;
+  a.arrived = reinterpret_cast<unsigned int*>(w.sync) + kSyncArrived;
+  a.epoch = epoch;
+  const int bx = max_blocks < 1 ? 1 : max_blocks;
+  pull_shards_kernel<<<bx, block_threads, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }
@@ -800,21 +970,6 @@ int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_b
     case 8: pull_reduce_kernel<8><<<blocks, block_threads, 0, stream>>>(a); break;
     default: pull_reduce_kernel<0><<<blocks, block_threads, 0, stream>>>(a); break;
   }
-  SCLIP_LAUNCHED();
-  return SCLIP_OK;
-}
-
-int launch_pull_stats(const Workspace& w, const void* const* peer_ws, uint64_t src_off, int count, float* out,
-                      bool sum_loss, cudaStream_t stream) {
-  PullStatsArgs a;
-  memset(&a, 0, sizeof(a));
-  for (int r = 0; r < w.pb.world; ++r) a.peer[r] = static_cast<const uint8_t*>(peer_ws[r]);
-  a.world = w.pb.world;
-  a.src_off = src_off;
-  a.out = out;
-  a.count = count;
-  if (sum_loss) pull_loss_kernel<<<1, 32, 0, stream>>>(a);
-  else pull_stats_kernel<<<dim3((count + 1023) / 1024 > 32 ? 32 : (count + 1023) / 1024, w.pb.world), 256, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }

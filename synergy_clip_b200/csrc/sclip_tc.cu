@@ -15,6 +15,7 @@
 // The 512 TMEM columns hold two 128x256 fp32 accumulators, so the epilogue of tile n runs under the MMAs of tile n+1.
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -403,6 +404,41 @@ __device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int
   return r;
 }
 
+// SCLIP_FWD_WAIT_PEERS: the tiles are taken wave by wave -- every (pair, row tile) on this rank's own columns first,
+// then on the columns of rank + 1, rank + 2, ... (the order in which sclip_pull_shards completes the shards).
+template <int CG>
+__device__ __forceinline__ Tile decode_forward(const FwdParams& P, int t, int npairs, int nti_c, int& wave) {
+  if (!P.wait_peers) {
+    wave = 0;
+    return decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
+  }
+  const int per_wave = npairs * nti_c * P.tiles_per_rank;
+  wave = t / per_wave;
+  return decode_similarity<CG>(t - wave * per_wave, nti_c, P.tiles_per_rank, P.tj_begin + wave * P.tiles_per_rank, P.ntj);
+}
+
+// Block until the shard of wave `wave` (source rank (rank + wave) % world) is complete in this workspace.
+__device__ __forceinline__ void wait_landed(const FwdParams& P, int wave) {
+  if (wave <= 0) return;
+  const int* flag = P.landed + (P.rank + wave) % P.world;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v - P.epoch >= 0) return;
+    __nanosleep(200);
+    if ((++spins & 0xFFF) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ull) {
+        printf("sclip: peer shard of wave %d never landed (block %d)\n", wave, static_cast<int>(blockIdx.x));
+        __trap();
+      }
+    }
+  }
+}
+
 template <int CG, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __grid_constant__ FwdParams P) {
   constexpr int S = EW / 4;        // column slices
@@ -426,6 +462,7 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) forward_tiles_kernel(const __
   int pairs[3] = {P.pair_list[0], P.pair_list[1], P.pair_list[2]};
   const int npairs = P.pair_filter ? select_pairs(P, false, pairs) : P.npairs;
   const int total = npairs * nti_c * P.tj_count;
+  if (total == 0) return;  // every pair was taken by forward_fast_kernel
 
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
@@ -728,24 +765,32 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
   int pairs[3];
   const int npairs = select_pairs(P, true, pairs);
   const int total = npairs * nti_c * P.tj_count;
+  if (total == 0 && !P.wait_peers) return;  // nothing for this kernel (every pair has s >= kFoldMaxScale)
 
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 
   if (warp == EW) {
     const bool elected = elect_one();
     RingState rs;
+    int landed_wave = 0;
     for (int t = cluster_id; t < total; t += num_clusters) {
-      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
+      int wave;
+      Tile tile = decode_forward<CG>(P, t, npairs, nti_c, wave);
       tile.job = pairs[tile.job];
+      for (; landed_wave < wave; ++landed_wave) wait_landed(P, landed_wave + 1);
       producer_tile<CG>(P.maps, P.jobs[tile.job], tile, rank, smem, &bars, P.stages, rs, elected);
     }
+    // a kernel launched behind this one (the s >= 44 pairs, the backward) may read every shard without checking
+    if (P.wait_peers)
+      for (; landed_wave < P.world - 1; ++landed_wave) wait_landed(P, landed_wave + 1);
   } else if (warp == EW + 1) {
     if (rank == 0) {  // the leader CTA issues the MMAs of the pair
       const bool elected = elect_one();
       RingState rs;
       int it = 0;
       for (int t = cluster_id; t < total; t += num_clusters, ++it) {
-        Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
+        int wave;
+        Tile tile = decode_forward<CG>(P, t, npairs, nti_c, wave);
         tile.job = pairs[tile.job];
         const int acc = it & 1;
         mma_tile<CG>(P.jobs[tile.job], tile, smem, &bars, P.stages, rs, tmem_base + acc * BN, acc, (it >> 1) & 1, elected);
@@ -764,8 +809,11 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
     const uint32_t st_chunk1 = static_cast<uint32_t>((((lane >> 3) + 4) ^ (lane & 7)) << 4);
 
     // positive-pair logits of a tile's rows / columns -> stash factors (loaded one tile ahead)
+    int landed_wave = 0;  // waves whose positive-pair logits may be read (WAIT_PEERS)
     auto tile_coords = [&](int t, int& p, int& ti, int& tj, int& m0, int& n0) {
-      Tile tile = decode_similarity<CG>(t, nti_c, P.tj_count, P.tj_begin, P.ntj);
+      int wave;
+      Tile tile = decode_forward<CG>(P, t, npairs, nti_c, wave);
+      for (; landed_wave < wave; ++landed_wave) wait_landed(P, landed_wave + 1);
       p = pairs[tile.job];
       ti = tile.ti * CG + static_cast<int>(rank);
       tj = tile.tj;
@@ -779,9 +827,9 @@ __global__ void __launch_bounds__(64 + 32 * 8, 1) forward_fast_kernel(const __gr
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int row = m0 + q * 32 + 16 * (j >> 1) + 8 * (j & 1) + (lane >> 2);
-        r4[j] = row < P.rows_local ? dg[P.row_offset + row] : 0.f;
+        r4[j] = row < P.rows_local ? __ldcg(dg + P.row_offset + row) : 0.f;
       }
-      c1 = (n0 + my_col < P.rows_global) ? dg[n0 + my_col] : 0.f;
+      c1 = (n0 + my_col < P.rows_global) ? __ldcg(dg + n0 + my_col) : 0.f;
     };
     float nxt_r[4] = {0.f, 0.f, 0.f, 0.f}, nxt_c = 0.f;  // raw positive-pair logits of the next tile
     float cur_r[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1495,6 +1543,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------- host launchers
+}  // namespace
+
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -1507,12 +1557,40 @@ int sm_count() {
   return cached;
 }
 
+namespace {
+
+// cudaFuncSetAttribute once per (kernel, device) instead of on every launch
+int ensure_smem_attribute(const void* kernel, int smem_bytes) {
+  struct Entry {
+    const void* fn;
+    int dev;
+    int bytes;
+  };
+  static Entry table[64];
+  static int used = 0;
+  static std::mutex mu;
+  int dev = 0;
+  SCLIP_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (table[i].fn == kernel && table[i].dev == dev) {
+      if (table[i].bytes >= smem_bytes) return SCLIP_OK;
+      SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      table[i].bytes = smem_bytes;
+      return SCLIP_OK;
+    }
+  SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (used < 64) table[used++] = Entry{kernel, dev, smem_bytes};
+  return SCLIP_OK;
+}
+
 template <class Params>
 int launch_persistent(void (*kernel)(Params), const Params& p, int cg, int ew, int smem_bytes, int total_cluster_tiles,
-                      cudaStream_t stream) {
-  SCLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+                      int max_sms, cudaStream_t stream) {
+  const int rc = ensure_smem_attribute(reinterpret_cast<const void*>(kernel), smem_bytes);
+  if (rc) return rc;
   int sms = sm_count();
-  if (max_sms() > 0 && max_sms() < sms) sms = max_sms();
+  if (max_sms > 0 && max_sms < sms) sms = max_sms;
   int clusters = sms / cg;
   if (total_cluster_tiles < clusters) clusters = total_cluster_tiles;
   if (clusters < 1) clusters = 1;
@@ -1552,7 +1630,7 @@ int tile_smem_bytes(int cg, int stages, int slabs) {
   return stages * stage_bytes + slabs * kSlabBytes + 1024;
 }
 
-int launch_forward_tiles(const FwdParams& p0, int cg, int ew, cudaStream_t stream) {
+int launch_forward_tiles(const FwdParams& p0, int cg, int ew, int max_sms, cudaStream_t stream) {
   FwdParams p = p0;
   const int smem = tile_smem_bytes(cg, p.stages, p.stash ? 4 : 0);
   const int total = p.npairs * (p.nti / cg) * p.tj_count;
@@ -1563,25 +1641,33 @@ int launch_forward_tiles(const FwdParams& p0, int cg, int ew, cudaStream_t strea
   }();
   if (cg == 2 && fast_on) {
     // pairs with s < kFoldMaxScale (decided on the device: the scales are never read by the host), then the rest
-    const int rc = p.stash ? launch_persistent(forward_fast_kernel<true>, p, 2, 8, smem, total, stream)
-                           : launch_persistent(forward_fast_kernel<false>, p, 2, 8, smem, total, stream);
+    const int rc = p.stash ? launch_persistent(forward_fast_kernel<true>, p, 2, 8, smem, total, max_sms, stream)
+                           : launch_persistent(forward_fast_kernel<false>, p, 2, 8, smem, total, max_sms, stream);
     if (rc) return rc;
     p.pair_filter = 1;
+    if (p.wait_peers) {  // forward_fast_kernel has waited for every shard: the rest runs in the plain column order
+      p.wait_peers = 0;
+      p.tj_begin = 0;
+      p.tj_count = p.ntj;
+    }
+  } else if (p.wait_peers) {
+    set_error("SCLIP_FWD_WAIT_PEERS needs the CTA-pair forward kernel (SCLIP_CTA_GROUP=2, SCLIP_FAST!=0)");
+    return SCLIP_ERR_UNSUPPORTED;
   }
-  SCLIP_DISPATCH(forward_tiles_kernel, smem, total, stream);
+  SCLIP_DISPATCH(forward_tiles_kernel, smem, total, max_sms, stream);
 }
 
 int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t stream) {
   const int smem = tile_smem_bytes(cg, p.stages, staging_slabs(ew, p.store_map_lo[0] >= 0));
   const int total = 3 * (p.nti / cg) * p.ntj;
-  SCLIP_DISPATCH(backward_tiles_kernel, smem, total, stream);
+  SCLIP_DISPATCH(backward_tiles_kernel, smem, total, 0, stream);
 }
 
-int launch_gemm(const GemmParams& p, int cg, int ew, cudaStream_t stream) {
+int launch_gemm(const GemmParams& p, int cg, int ew, int max_sms, cudaStream_t stream) {
   const int smem = tile_smem_bytes(cg, p.stages, 0);
   const int total = p.total_tiles;
   if (total <= 0) return SCLIP_OK;
-  SCLIP_DISPATCH(gemm_tiles_kernel, smem, total, stream);
+  SCLIP_DISPATCH(gemm_tiles_kernel, smem, total, max_sms, stream);
 }
 
 int wide_stages(int wn) {
@@ -1589,15 +1675,15 @@ int wide_stages(int wn) {
   return st > kMaxStages ? kMaxStages : st;
 }
 
-int launch_gemm_wide(const GemmParams& p, int ew, cudaStream_t stream) {
+int launch_gemm_wide(const GemmParams& p, int ew, int max_sms, cudaStream_t stream) {
   if (p.total_tiles <= 0) return SCLIP_OK;
   if (p.wn != 256 && p.wn != 384 && p.wn != 512) {
     set_error("internal: wide GEMM tile width %d", p.wn);
     return SCLIP_ERR_ARGUMENT;
   }
   const int smem = p.stages * (A_STAGE_BYTES + p.wn * 64) + 1024;
-  if (ew == 16) return launch_persistent(gemm_wide_kernel<16>, p, 2, 16, smem, p.total_tiles, stream);
-  return launch_persistent(gemm_wide_kernel<8>, p, 2, 8, smem, p.total_tiles, stream);
+  if (ew == 16) return launch_persistent(gemm_wide_kernel<16>, p, 2, 16, smem, p.total_tiles, max_sms, stream);
+  return launch_persistent(gemm_wide_kernel<8>, p, 2, 8, smem, p.total_tiles, max_sms, stream);
 }
 
 }  // namespace sclip

@@ -44,8 +44,8 @@ class TriContrastiveConfig:
     """
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
-                 overlap: bool = True, comm_sms: int = 20, stash="auto", fuse_scale: bool = False,
-                 transport: str = "auto"):
+                 overlap: bool = True, comm_sms: int = 20, stash="auto", transport: str = "auto",
+                 check_status: bool = False):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -62,10 +62,6 @@ class TriContrastiveConfig:
         if stash not in ("auto", True, False):
             raise ValueError(f"stash={stash!r}")
         self.stash = stash
-        # (round 1 also tried converting the stash inside the gradient GEMMs, `fuse_scale`: 3.4 ms more GEMM time for a
-        # 2.4 ms pass saved, and no place for the fp32 identity term of `sclip_backward_scale`; the code is at commit 5c56fe2)
-        if fuse_scale:
-            raise ValueError("fuse_scale was a round-1 experiment and has been removed (see DESIGN.md section 9)")
         # world_size > 1: how the shards move between ranks.
         #   "p2p"  -- the workspace lives in symmetric memory (torch.distributed._symmetric_memory: every rank's blob
         #             mapped into every process over NVLink / NVSwitch) and the exchanges are kernels of the library
@@ -76,6 +72,10 @@ class TriContrastiveConfig:
         if transport not in ("auto", "p2p", "nccl"):
             raise ValueError(f"transport={transport!r}")
         self.transport = transport
+        # Read the device status word after every forward (one host synchronisation per call) and raise if a row or
+        # column log-sum-exp was not finite.  Off by default: the losses are non-finite too in that case, which the
+        # caller's own `.item()` (main_pretraining.py:169-170) shows without an extra sync.
+        self.check_status = check_status
 
 
 _DEFAULT = TriContrastiveConfig()
@@ -166,6 +166,12 @@ class _Workspace:
         raw = torch.empty(int(self.lay.total_bytes) + 256, dtype=torch.uint8, device=device)
         skew = (-raw.data_ptr()) % 256  # the ABI wants a 256-byte aligned blob
         self.blob = raw[skew:skew + int(self.lay.total_bytes)]
+        self._init_sync()
+
+    def _init_sync(self):
+        """The flags / counters of the `sync` area live across calls: the owner zeroes them once (include/sclip.h)."""
+        self.epoch = 0  # grows by one per sharded forward: the "shard landed" flags are compared against it
+        self.blob[int(self.lay.sync):int(self.lay.sync) + 256].zero_()
 
     def view(self, offset: int, shape, dtype: torch.dtype) -> torch.Tensor:
         n = 1
@@ -195,6 +201,7 @@ class _SymmWorkspace(_Workspace):
         self.hdl = symm.rendezvous(raw, group)
         self._raw = raw
         self.blob = raw[:nbytes]
+        self._init_sync()
         ptrs = list(self.hdl.buffer_ptrs)
         self.peer_ptrs = (ctypes.c_void_p * len(ptrs))(*ptrs)
         self.group = group
@@ -380,44 +387,35 @@ class _CudaBackend:
             self._lib = _lib.load()
         return self._lib
 
-    def prologue(self, ws, img, txt, aud):
-        _lib.check(self.lib.sclip_prologue(byref(ws.pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _stream()),
-                   "sclip_prologue")
+    def prologue(self, ws, img, txt, aud, t3=None, diag=False):
+        """normalise + cast; diag: also the positive-pair logits of this rank's rows (what a stash forward needs)"""
+        _lib.check(self.lib.sclip_prologue(byref(ws.pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3),
+                                           1 if diag else 0, _stream()), "sclip_prologue")
 
-    def forward_tiles(self, ws, t3):
-        _lib.check(self.lib.sclip_forward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_tiles")
-
-    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False, wrap=False):
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False, wrap=False, max_sms=0,
+                           wait_epoch=None):
+        flags = (1 if stash else 0) | (2 if wrap else 0) | (4 if wait_epoch is not None else 0)
         _lib.check(self.lib.sclip_forward_tiles_cols(byref(ws.pb), ws.ptr, _ptr(t3), int(pair_mask), int(tile_lo),
-                                                     int(tile_hi), (1 if stash else 0) | (2 if wrap else 0),
+                                                     int(tile_hi), flags, int(max_sms), int(wait_epoch or 0),
                                                      _stream()),
                    "sclip_forward_tiles_cols")
-
-    def forward_diag(self, ws, t3):
-        _lib.check(self.lib.sclip_forward_diag(byref(ws.pb), ws.ptr, _ptr(t3), _stream()), "sclip_forward_diag")
 
     def backward_scale(self, ws, t3, g3):
         _lib.check(self.lib.sclip_backward_scale(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
                    "sclip_backward_scale")
 
-    def backward_gemms_role(self, ws, t3, g3, role):
-        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), 0,
+    def backward_gemms_role(self, ws, t3, g3, role, max_sms=0):
+        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), int(max_sms),
                                                       _stream()), "sclip_backward_gemms_role")
 
-    def set_max_sms(self, n):
-        return self.lib.sclip_set_max_sms(int(n))
-
-    def pull_shards(self, ws, first, count, max_blocks, block_threads=1024):
+    def pull_shards(self, ws, first, count, max_blocks, block_threads=1024, epoch=0):
         _lib.check(self.lib.sclip_pull_shards(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(first), int(count),
-                                              int(max_blocks), int(block_threads), _stream()), "sclip_pull_shards")
+                                              int(max_blocks), int(block_threads), int(epoch), _stream()),
+                   "sclip_pull_shards")
 
-    def pull_col_lse(self, ws, col_all):
-        _lib.check(self.lib.sclip_pull_col_lse(byref(ws.pb), ws.ptr, ws.peer_ptrs, _ptr(col_all), _stream()),
-                   "sclip_pull_col_lse")
-
-    def pull_loss(self, ws, loss3):
-        _lib.check(self.lib.sclip_pull_loss(byref(ws.pb), ws.ptr, ws.peer_ptrs, _ptr(loss3), _stream()),
-                   "sclip_pull_loss")
+    def forward_loss_peers(self, ws, loss3):
+        _lib.check(self.lib.sclip_forward_loss_peers(byref(ws.pb), ws.ptr, ws.peer_ptrs, _ptr(loss3), _stream()),
+                   "sclip_forward_loss_peers")
 
     def pull_reduce_cols(self, ws, max_blocks, block_threads=512):
         _lib.check(self.lib.sclip_pull_reduce_cols(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(max_blocks),
@@ -434,10 +432,6 @@ class _CudaBackend:
         _lib.check(self.lib.sclip_backward_tiles(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
                    "sclip_backward_tiles")
 
-    def backward_gemms(self, ws, t3, g3):
-        _lib.check(self.lib.sclip_backward_gemms(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
-                   "sclip_backward_gemms")
-
     def backward_finish(self, ws, img, txt, aud, t3, g3, col, mult, dimg, dtxt, daud, out_f32, dt3, stashed=False):
         _lib.check(
             self.lib.sclip_backward_finish(byref(ws.pb), ws.ptr, _ptr(img), _ptr(txt), _ptr(aud), _ptr(t3), _ptr(g3),
@@ -445,13 +439,32 @@ class _CudaBackend:
                                            int(out_f32), 1 if stashed else 0, _ptr(dt3), _stream()),
             "sclip_backward_finish")
 
+    def read_status(self, ws):
+        words = (ctypes.c_int32 * 4)()
+        _lib.check(self.lib.sclip_read_status(byref(ws.pb), ws.ptr, words, _stream()), "sclip_read_status")
+        return list(words)
+
 
 # The stage executor.  The package ships exactly one (CUDA); the world_size > 1 CPU tests substitute a test double
 # from tests/ to exercise the collective choreography below under the gloo backend.
 _BACKEND = _CudaBackend()
 
 
+def _check_status(ws: _Workspace, cfg: TriContrastiveConfig) -> None:
+    if cfg.check_status and not _BACKEND.allows_cpu:
+        words = _BACKEND.read_status(ws)
+        if words[0] != 0:
+            raise _lib.SclipError("a row or column log-sum-exp of the contrastive forward is not finite (non-finite "
+                                  "embeddings, or exp(logit_scale) beyond the fp32 range): the losses are not finite")
+
+
 def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, keep: bool = False) -> torch.Tensor:
+    loss3 = _forward_stages(ws, img, txt, aud, t3, cfg, keep)
+    _check_status(ws, cfg)
+    return loss3
+
+
+def _forward_stages(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, keep: bool = False) -> torch.Tensor:
     """keep: a backward will follow on this workspace.  With fp16 operands the forward then also stores the scaled
     exponentials of every tile (the "stash") so that the backward does not recompute the similarity matrices."""
     be = _BACKEND
@@ -459,9 +472,7 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
     stash = bool(keep) and pb.math == MATH_F16 and (pb.dim >= 640 if cfg.stash == "auto" else bool(cfg.stash))
     ws.stashed = stash
     _mark("begin")
-    be.prologue(ws, img, txt, aud)
-    if stash:
-        be.forward_diag(ws, t3)
+    be.prologue(ws, img, txt, aud, t3, diag=stash)
     _mark("prologue")
     loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
     if pb.world == 1:
@@ -508,11 +519,7 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
             _all_gather(pieces, pg, True)
             landed.record(comm)
         lo, hi = off // 256, (off + bl) // 256
-        prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
-        try:
-            be.forward_tiles_cols(ws, t3, 7, lo, hi, stash)
-        finally:
-            be.set_max_sms(prev)
+        be.forward_tiles_cols(ws, t3, 7, lo, hi, stash, max_sms=_sm_count(img.device) - cfg.comm_sms)
         cur.wait_event(landed)
         be.forward_tiles_cols(ws, t3, 7, 0, lo, stash)
         be.forward_tiles_cols(ws, t3, 7, hi, lay.col_tiles, stash)
@@ -528,103 +535,57 @@ def _forward_impl(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig, 
     return loss3
 
 
-def _pull_waves(world: int, pipelined: bool):
-    """How many ranks each pull wave brings in: 1, 2, 4, ... (the first wave lands under the tiles of this rank's own
-    columns, each following one under the tiles of the wave before it); one wave of everything when not pipelined."""
-    waves, left = [], world - 1
-    while left > 0:
-        n = min(left, 1 << len(waves)) if pipelined else left
-        waves.append(n)
-        left -= n
-    return waves
-
-
-def _wave_column_ranges(world: int, rank: int, tiles_per_rank: int, waves):
-    """(first column tile, tile count) of this rank's own columns and of every wave, in launch order.  Wave i holds the
-    columns of ranks rank + 1 + (ranks of earlier waves) ..., modulo world: a range may wrap around the last column
-    tile (the tile kernels take it modulo the tile count, SCLIP_FWD_WRAP)."""
-    col_tiles = world * tiles_per_rank
-    out = [(rank * tiles_per_rank, tiles_per_rank)]
-    begin = ((rank + 1) % world) * tiles_per_rank
-    for n in waves:
-        out.append((begin, n * tiles_per_rank))
-        begin = (begin + n * tiles_per_rank) % col_tiles
-    return out
-
-
 def _forward_p2p(ws: "_SymmWorkspace", t3, cfg: TriContrastiveConfig, stash: bool, loss3: torch.Tensor):
     """world > 1, workspace in symmetric memory.  After the prologue the operand shards of the other ranks are pulled
-    over NVLink by `sclip_pull_shards` in two waves on the side stream while the tiles of the columns already present
-    run: own columns, then the first wave's, then the second wave's.  Barriers are the symmetric-memory signal pads
-    (channel 0 on the side stream, 1 and 2 on the compute stream)."""
+    over NVLink by ONE `sclip_pull_shards` launch on the side stream (rank + 1 first, then rank + 2, ...), which
+    publishes a per-rank "landed" flag as each shard completes.  The similarity tiles are ONE persistent launch as well
+    (`SCLIP_FWD_WAIT_PEERS`): it takes this rank's own columns first and then the peers' in the same order, its TMA
+    producer acquiring the flag of a rank before the first tile on that rank's columns -- no host-side waves, no
+    per-wave launch / ramp / tail.  The pull kernel runs on the `comm_sms` SMs the tile kernel leaves free.
+    Barriers are the symmetric-memory signal pads (channel 0 on the side stream, 1 on the compute stream).
+
+    Cross-step ordering: a rank overwrites its shard (prologue) and its column statistics (forward_reduce) only after
+    every peer has finished reading the previous step's -- the peers' pulls complete before their tiles do, their
+    tiles before barrier 1, and barrier 0 of the next step follows every rank's `sclip_forward_loss_peers`."""
     be = _BACKEND
     pb, lay, hdl = ws.pb, ws.lay, ws.hdl
-    bl, off, world = pb.rows_local, pb.row_offset, pb.world
+    bl, world = pb.rows_local, pb.world
     dev = ws.blob.device
     cur = torch.cuda.current_stream()
     comm = _comm_stream(dev)
-    tiles_per_rank = bl // 256
-    pipelined = cfg.overlap and bl % 256 == 0
-    # pull kernels: 1024-thread blocks, two per SM left free by the tile kernels (comm_sms > 0), or -- comm_sms == 0 --
-    # 256-thread blocks, one per SM, which fit beside a resident persistent tile CTA (no SM is taken from the tiles).
-    # Measured at 8 GPUs (B = 32768, D = 768): 2.71-2.82 ms/step with 20 reserved SMs, 2.95 with 12, 3.05 co-resident:
-    # the pulls are slower beside busy tile warps than the tiles are faster on 20 more SMs.
-    coresident = cfg.comm_sms == 0
-    blocks = _sm_count(dev) if coresident else 2 * max(cfg.comm_sms, 4)
-    pull_threads = 256 if coresident else 1024
+    # the in-kernel wait needs the pull kernel to be resident next to the tile kernel: it gets its own SMs
+    pipelined = cfg.overlap and bl % 256 == 0 and cfg.comm_sms > 0
+    # pull kernel: 1024-thread blocks, two per SM left free by the tile kernel.  Measured at 8 GPUs (B = 32768, D = 768):
+    # 20 reserved SMs beat 12, and 256-thread blocks co-resident with the tile CTAs (no reserved SMs) were slower still.
+    blocks = 2 * max(cfg.comm_sms, 4)
+    ws.epoch += 1
     ready = torch.cuda.Event()
     ready.record(cur)
-    waves = _pull_waves(world, pipelined)
     trace = _TRACE is not None
-    landed = [torch.cuda.Event(enable_timing=trace) for _ in waves]
+    pulled = torch.cuda.Event(enable_timing=trace)
     after_barrier = torch.cuda.Event(enable_timing=True) if trace else None
-
-    def start_pulls():
-        with torch.cuda.stream(comm):
-            comm.wait_event(ready)
-            hdl.barrier(0)  # every rank's own shard is normalised and in place
-            if trace:
-                after_barrier.record(comm)
-            first = 1
-            for n, ev in zip(waves, landed):
-                be.pull_shards(ws, first, n, blocks, pull_threads)
-                ev.record(comm)
-                first += n
+    with torch.cuda.stream(comm):
+        comm.wait_event(ready)
+        hdl.barrier(0)  # every rank's own shard is normalised and in place
         if trace:
-            global _LAST_COMM_EVENTS
-            _LAST_COMM_EVENTS = [("fwd_barrier", after_barrier)] + [(f"pull{i + 1}", ev) for i, ev in enumerate(landed)]
-
+            after_barrier.record(comm)
+        be.pull_shards(ws, 1, world - 1, blocks, 1024, ws.epoch)
+        pulled.record(comm)
+    if trace:
+        global _LAST_COMM_EVENTS
+        _LAST_COMM_EVENTS = [("fwd_barrier", after_barrier), ("pulls", pulled)]
     if pipelined:
-        ranges = _wave_column_ranges(world, off // bl, tiles_per_rank, waves)
-        prev = be.set_max_sms(_sm_count(dev) - cfg.comm_sms)  # the pull kernels run on the SMs left free
-        try:
-            be.forward_tiles_cols(ws, t3, 7, ranges[0][0], ranges[0][0] + ranges[0][1], stash)
-            start_pulls()
-            _mark("forward_tiles_local")
-            for i, ((begin, count), ev) in enumerate(zip(ranges[1:], landed)):
-                cur.wait_event(ev)
-                if i == len(waves) - 1:
-                    be.set_max_sms(prev)  # nothing left to pull: the last (largest) wave's tiles take every SM
-                be.forward_tiles_cols(ws, t3, 7, begin, begin + count, stash, wrap=True)
-                if i < len(waves) - 1:
-                    _mark(f"forward_tiles_wave{i + 1}")
-        finally:
-            be.set_max_sms(prev)
+        be.forward_tiles_cols(ws, t3, 7, 0, 0, stash, max_sms=_sm_count(dev) - cfg.comm_sms, wait_epoch=ws.epoch)
+        cur.wait_event(pulled)  # (already implied by the kernel's own waits; keeps the stream order explicit)
     else:
-        start_pulls()
-        cur.wait_event(landed[-1])
+        cur.wait_event(pulled)
         be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
     _mark("forward_tiles")
     be.forward_reduce(ws)
     _mark("forward_reduce")
-    # column statistics of every rank, read from the peers; then this rank's loss share, summed the same way
-    col_all = torch.empty((world, 3, pb.rows_global), dtype=torch.float32, device=dev)
-    hdl.barrier(1)
+    hdl.barrier(1)  # every rank's column statistics and row terms are complete
     _mark("forward_barrier1")
-    be.pull_col_lse(ws, col_all)
-    be.forward_loss(ws, col_all, None)
-    hdl.barrier(2)
-    be.pull_loss(ws, loss3)
+    be.forward_loss_peers(ws, loss3)  # merged column statistics + the complete losses, read from the peers
     _mark("forward_finish")
     return loss3
 
@@ -684,12 +645,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             if trace:
                 global _LAST_COMM_EVENTS
                 _LAST_COMM_EVENTS = (_LAST_COMM_EVENTS or []) + [("bwd_barrier", bar_done), ("pull_reduce", reduced)]
-            prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms) if cfg.overlap else None
-            try:
-                be.backward_gemms_role(ws, t3, g3, 2)
-            finally:
-                if prev is not None:
-                    be.set_max_sms(prev)
+            be.backward_gemms_role(ws, t3, g3, 2, max_sms=(_sm_count(img.device) - cfg.comm_sms) if cfg.overlap else 0)
             _mark("backward_gemms_row")
             cur.wait_event(reduced)
             _mark("backward_gemms")
@@ -709,11 +665,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
                 scatter()                            # ... its reduce-scatter runs under the row-role GEMMs
                 reduced = torch.cuda.Event()
                 reduced.record(comm)
-            prev = be.set_max_sms(_sm_count(img.device) - cfg.comm_sms)
-            try:
-                be.backward_gemms_role(ws, t3, g3, 2)
-            finally:
-                be.set_max_sms(prev)
+            be.backward_gemms_role(ws, t3, g3, 2, max_sms=_sm_count(img.device) - cfg.comm_sms)
             cur.wait_event(reduced)
             _mark("backward_gemms")
         if cfg.grad_scale == "ddp":

@@ -39,7 +39,7 @@ class EmulatedBackend:
         return hi
 
     # ------------------------------------------------------------------ forward
-    def prologue(self, ws, img, txt, aud):
+    def prologue(self, ws, img, txt, aud, t3=None, diag=False):
         bl, bg, d, off = self._dims(ws)
         hi = ws.view(ws.lay.xhat, (3, bg, d), torch.float16)
         inv = ws.view(ws.lay.inv_norm, (3, bl), torch.float32)
@@ -56,6 +56,8 @@ class EmulatedBackend:
             else:
                 hi[m, off:off + bl] = xh.half()
         ws.view(ws.lay.status, (4,), torch.int32).zero_()
+        if diag:
+            self.forward_diag(ws, t3)
 
     def _logits(self, ws, t3, p):
         bl, bg, d, off = self._dims(ws)
@@ -74,7 +76,8 @@ class EmulatedBackend:
         for p, (r, c) in enumerate(PAIRS):
             dg[p, off:off + bl] = (math.exp(float(t3[p])) * (xh[r, off:off + bl] * xh[c, off:off + bl]).sum(-1)).float()
 
-    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False):
+    def forward_tiles_cols(self, ws, t3, pair_mask, tile_lo, tile_hi, stash=False, wrap=False, max_sms=0,
+                           wait_epoch=None):
         """Column tiles [tile_lo, tile_hi) of the pairs in pair_mask; row partials land in slot `tile_lo`."""
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
@@ -185,13 +188,10 @@ class EmulatedBackend:
             g = g + ws.view(lay.grad_tiles_lo, (3, bl, lay.ld_g), torch.float16)[:, :, :bg].double()
         return g
 
-    def set_max_sms(self, n):
-        return 0
-
     def backward_gemms(self, ws, t3, g3):
         self.backward_gemms_role(ws, t3, g3, 0)
 
-    def backward_gemms_role(self, ws, t3, g3, role):
+    def backward_gemms_role(self, ws, t3, g3, role, max_sms=0):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
         mx, _ = self._coeffs(t3, g3)

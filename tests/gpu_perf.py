@@ -31,8 +31,7 @@ def step(b, d, iters):
     ten = [torch.randn(b, d, device="cuda", dtype=torch.bfloat16) for _ in range(3)]
     t3 = torch.full((3,), 2.6592, device="cuda")
     g3 = torch.ones(3, device="cuda")
-    cfg = ops.TriContrastiveConfig(math="f16", stash={"1": True, "0": False}.get(os.environ.get("SCLIP_STASH", "auto"), "auto"),
-                                   fuse_scale=os.environ.get("SCLIP_FUSE", "0") == "1")
+    cfg = ops.TriContrastiveConfig(math="f16", stash={"1": True, "0": False}.get(os.environ.get("SCLIP_STASH", "auto"), "auto"))
     ms = timed(lambda: ops.forward_backward_raw(*ten, t3, g3, cfg), iters)
     import time
     torch.cuda.synchronize()

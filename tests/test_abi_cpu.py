@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), name
     assert set(names) == set(_lib.EXPORTS)
-    assert lib.sclip_abi_version() == 1
+    assert lib.sclip_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_plan_layout_is_consistent():
@@ -83,9 +83,21 @@ def test_peer_memory_and_scorer_calls_validate_their_arguments():
     fake_ws = ctypes.c_void_p(1 << 20)                                                         # 256-byte aligned, never touched
     single = _lib.Problem(128, 128, 0, 512, 1, 0, 1, 0)
     table = (ctypes.c_void_p * 2)(1 << 20, 2 << 20)
-    assert lib.sclip_pull_shards(ctypes.byref(single), fake_ws, table, 1, 1, 8, 256, None) == -1    # world must be >= 2
+    assert lib.sclip_pull_shards(ctypes.byref(single), fake_ws, table, 1, 1, 8, 256, 1, None) == -1  # world must be >= 2
     sharded = _lib.Problem(128, 256, 128, 512, 1, 0, 2, 0)                                     # rank 1 of 2
-    assert lib.sclip_pull_shards(ctypes.byref(sharded), fake_ws, table, 1, 1, 8, 256, None) == -1   # peer_ws[rank] != ws
+    assert lib.sclip_pull_shards(ctypes.byref(sharded), fake_ws, table, 1, 1, 8, 256, 1, None) == -1  # peer_ws[rank] != ws
     assert b"own workspace" in lib.sclip_last_error()
     assert lib.sclip_pull_reduce_cols(ctypes.byref(sharded), fake_ws, None, 8, 256, None) == -1
+    assert lib.sclip_forward_loss_peers(ctypes.byref(sharded), fake_ws, None, None, None) == -1
+    # the single-launch forward (SCLIP_FWD_WAIT_PEERS = 4) needs equal shards that are multiples of 256 rows
+    t3 = ctypes.c_void_p(4 << 20)
+    assert lib.sclip_forward_tiles_cols(ctypes.byref(sharded), fake_ws, t3, 7, 0, 0, 4, 128, 1, None) == -1
+    assert b"multiples of 256" in lib.sclip_last_error()
+    assert lib.sclip_forward_tiles_cols(ctypes.byref(single), fake_ws, t3, 7, 0, 0, 4, 128, 1, None) == -1
+    # stash prologue flag (SCLIP_PRO_DIAG = 1) without the scales / a second backward without a forward
+    x = ctypes.c_void_p(8 << 20)
+    assert lib.sclip_prologue(ctypes.byref(single), fake_ws, x, x, x, None, 1, None) == -1
+    assert lib.sclip_backward(ctypes.byref(single), fake_ws, x, x, x, t3, t3, x, x, x, 0, t3, None) == -1
+    assert b"preceding sclip_forward" in lib.sclip_last_error()
+    assert lib.sclip_read_status(ctypes.byref(single), fake_ws, None, None) == -1
     assert lib.sclip_kernel_launches() == 0                                                    # nothing was launched

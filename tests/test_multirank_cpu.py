@@ -177,33 +177,34 @@ def test_ddp_wrapper_averages_to_the_global_batch_gradient(tmp_path):
         assert err < 1e-5, (k, float(err))
 
 
-@pytest.mark.parametrize("world", [2, 3, 4, 5, 6, 7, 8, 16])
-def test_pull_waves_cover_every_column_tile_exactly_once(world):
-    """Host logic of the peer-memory forward: the pull waves bring in every other rank exactly once, in the order
-    rank + 1, rank + 2, ... (the order `sclip_pull_shards` copies them), and the column-tile ranges handed to the tile
-    kernel -- own columns first, then wave by wave, wrapping around the last tile -- partition the column tiles."""
-    from synergy_clip_b200 import ops
-
-    tiles_per_rank = 3
+def _wave_major_order(world, rank, tiles_per_rank, npairs, row_tiles):
+    """Python restatement of decode_forward (csrc/sclip_tc.cu) for SCLIP_FWD_WAIT_PEERS: linear tile id -> (wave, pair,
+    row tile, column tile), grouped rasterisation inside a wave."""
     col_tiles = world * tiles_per_rank
-    for pipelined in (True, False):
-        waves = ops._pull_waves(world, pipelined)
-        assert sum(waves) == world - 1 and all(n >= 1 for n in waves)
-        if pipelined:
-            assert waves[0] == 1 and all(b <= 2 * a for a, b in zip(waves, waves[1:]))
-        else:
-            assert len(waves) == 1
-        for rank in range(world):
-            ranges = ops._wave_column_ranges(world, rank, tiles_per_rank, waves)
-            seen = []
-            for begin, count in ranges:
-                assert 0 <= begin < col_tiles and 0 < count <= col_tiles
-                seen += [(begin + k) % col_tiles for k in range(count)]
-            assert sorted(seen) == list(range(col_tiles))
-            assert seen[:tiles_per_rank] == [rank * tiles_per_rank + k for k in range(tiles_per_rank)]
-            # wave i's columns belong to the ranks its pull copied: rank + 1 + (ranks of the earlier waves) ...
-            first = 1
-            for (begin, count), n in zip(ranges[1:], waves):
-                owners = sorted({((begin + k) % col_tiles) // tiles_per_rank for k in range(count)})
-                assert owners == sorted((rank + first + i) % world for i in range(n))
-                first += n
+    per_wave = npairs * row_tiles * tiles_per_rank
+    out = []
+    for t in range(world * per_wave):
+        wave, r = divmod(t, per_wave)
+        pair, r = divmod(r, row_tiles * tiles_per_rank)
+        group, r = divmod(r, 8 * tiles_per_rank)
+        first = group * 8
+        gm = min(row_tiles - first, 8)
+        ti, tj = first + r % gm, r // gm
+        tj = (rank * tiles_per_rank + wave * tiles_per_rank + tj) % col_tiles
+        out.append((wave, pair, ti, tj))
+    return out
+
+
+@pytest.mark.parametrize("world,row_tiles", [(2, 8), (3, 5), (4, 16), (8, 8), (16, 3)])
+def test_wave_major_tile_order_matches_the_pull_order(world, row_tiles):
+    """Host-side model of the single-launch peer-memory forward: every (pair, row tile, column tile) is taken exactly
+    once, wave w only touches the columns of rank + w -- the shard `sclip_pull_shards` completes w-th -- and wave 0 is
+    this rank's own columns, so the kernel never needs a shard earlier than the pull kernel delivers it."""
+    tiles_per_rank, npairs = 3, 3
+    for rank in range(world):
+        order = _wave_major_order(world, rank, tiles_per_rank, npairs, row_tiles)
+        assert len(set((p, ti, tj) for _, p, ti, tj in order)) == len(order) == npairs * row_tiles * world * tiles_per_rank
+        waves = [w for w, _, _, _ in order]
+        assert waves == sorted(waves)
+        for wave, _, _, tj in order:
+            assert tj // tiles_per_rank == (rank + wave) % world

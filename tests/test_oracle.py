@@ -63,3 +63,21 @@ def test_live_reference_agrees_with_oracle():
     mine = closed_form.tri_contrastive(*embs, t3, g3)
     for k in ("loss", "dscale", "dimg", "dtxt", "daud"):
         assert golden_util.rel(mine[k], ref[k]) < 1e-12, k
+
+
+@pytest.mark.parametrize("name,block", [("cfg1_256x512_weighted", 100), ("ragged_35x768", 16), ("b2048x512_planted", 512),
+                                        ("b300x512_ln100", 128)])
+def test_blockwise_oracle_matches_reference_golden(name, block):
+    """oracle/blockwise.py (the full-size oracle of tests/test_gpu_fullsize.py: B x B never held whole, gradients for a
+    sample of rows) against the vectors the unmodified reference produced, and against the dense closed form."""
+    from oracle import blockwise
+
+    meta, embs, data = golden_util.load_case(name)
+    rows = data["rows"]
+    got = blockwise.tri_contrastive_rows(*embs, meta["t3"], meta["g3"], rows, block=block)
+    assert np.max(np.abs(got["loss"].numpy() - data["loss"]) / np.abs(data["loss"])) < 1e-12
+    assert np.max(np.abs(got["dscale"].numpy() - data["dscale"])) / np.max(np.abs(data["dscale"])) < 1e-9
+    dense = closed_form.tri_contrastive(*embs, meta["t3"], meta["g3"])
+    for key in ("dimg", "dtxt", "daud"):
+        assert golden_util.rel(got[key + "_rows"].numpy(), data[key + "_rows"]) < 2e-7, key   # fixtures are fp32
+        assert golden_util.rel(got[key + "_rows"].numpy(), dense[key][rows]) < 1e-12, key

@@ -2,13 +2,18 @@
 """Benchmark of the fused tri-modal contrastive objective (BASELINE.json metric: fwd+bwd samples/s, % of
 tensor-core peak).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N ...            # the reference's PyTorch CPU loss path (oracle port)
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, north-star workload
+    python bench.py --workload cfg1|cfg2|north_star          # BASELINE.json configs 1-3 as the headline of the line
+    python bench.py --workload sweep [--gpus N]              # BASELINE config 5: B x D sweep, one JSON line per point
+                                                             # into gpurun_out/sweep_w<N>.jsonl (+ one summary line)
+    python bench.py --impl reference [--workload ...]        # the reference's PyTorch CPU loss path (oracle port)
 
 One "step" = one forward + backward of the loss tail (model.py:247-272 + autograd) over one synthetic global
-batch.  Workload (every N, strong scaling): the north-star shape B=32768, D=768, bf16 embeddings, row-sharded
-over the N ranks.  The BASELINE config-2 shape (8192 x 512, single GPU) is timed in the same run and reported
-under "also".  Prints exactly one JSON line on rank 0.
+batch.  Default workload (every N, strong scaling): the north-star shape B=32768, D=768, bf16 embeddings, row-sharded
+over the N ranks; at N=1 the same run also reports config 2 (8192 x 512 bf16), config 1 (256 x 512 fp32, with the CPU
+baseline timed for real on that shape: 5 + 30 iterations), the CPU baseline of the north-star
+shape (a bounded sub-batch, EXTRAPOLATED, labelled as such) and the reference's own tail under torch eager on the same
+GPU (`gpu_eager_baseline`: "the existing kernels on the same box").  Prints exactly one JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -24,12 +29,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 LOGIT_SCALE_INIT = 2.6592  # config.py:112
-WORKLOADS = {"north_star": (32768, 768), "cfg2": (8192, 512)}
-CPU_SAMPLE_ROWS = 4096  # bounded CPU sample: a 4096-row sub-batch of the same embeddings
+WORKLOADS = {"north_star": (32768, 768, "bf16"), "cfg2": (8192, 512, "bf16"), "cfg1": (256, 512, "f32")}
+CPU_SAMPLE_ROWS = 4096  # bounded CPU sample of the large workloads: a 4096-row sub-batch of the same embeddings
+SWEEP_B = (4096, 8192, 16384, 32768, 65536, 131072)
+SWEEP_D = (512, 768, 1024)
 
 
 def load_traffic(b, d, world):
-    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed `ncu --set full` capture."""
+    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed `ncu --set full` capture (a
+    profiler figure cannot be taken inside a timed run; the capture is of this workload at one GPU only)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
@@ -146,25 +154,46 @@ def cpu_full_batch_rate(rows: int, b: int, dt: float) -> float:
     return b / (dt * (b / rows) ** 2)
 
 
+def cpu_block(b: int, d: int, steps: int, warmup: int):
+    """cpu_baseline object for a workload.  b <= CPU_SAMPLE_ROWS: the reference functions timed for real on that shape.
+    Larger: a CPU_SAMPLE_ROWS-row sub-batch (the full batch needs nine B x B fp32 matrices: 36 GiB at 32768), scaled
+    by the quadratic work ratio and LABELLED extrapolated."""
+    rows = min(CPU_SAMPLE_ROWS, b)
+    sub_rate, dt, threads = cpu_tail_rate(rows, d, steps, warmup)
+    if rows == b:
+        return {"value": sub_rate, "unit": "samples/s", "cores": threads, "kind": "port", "extrapolated": False,
+                "ms_per_step": dt * 1e3,
+                "sample": f"the whole {b}x{d} workload, fp32 torch CPU on {threads} threads, {warmup} warm-up + {steps} "
+                          f"timed fwd+bwd steps of the reference's statements (oracle/reference_tail.py = "
+                          f"model.py:247-272), {dt * 1e3:.2f} ms/step"}, dt
+    rate = cpu_full_batch_rate(rows, b, dt)
+    return {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "extrapolated": True,
+            "ms_per_step": dt * 1e3 * (b / rows) ** 2,
+            "sample": f"EXTRAPOLATED: {warmup} warm-up + {steps} timed fwd+bwd steps of a {rows}-row sub-batch of the "
+                      f"{b}x{d} workload (fp32 torch CPU, {threads} threads, {dt:.2f} s/step = {sub_rate:.0f} samples/s "
+                      f"at B={rows}), scaled by the quadratic work ratio (B/{rows})^2; the full batch itself needs nine "
+                      f"B x B fp32 matrices"}, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    b, d = WORKLOADS[args.workload]
-    rows = min(CPU_SAMPLE_ROWS, b)
-    sub_rate, dt, threads = cpu_tail_rate(rows, d, args.steps, args.warmup)
-    rate = cpu_full_batch_rate(rows, b, dt)
-    sample = (f"each step = fwd+bwd of a {rows}-row sub-batch of the {b}x{d} workload (fp32, torch CPU, {threads} "
-              f"threads, {dt:.2f} s/step = {sub_rate:.0f} samples/s at B={rows}); value is that time scaled by the "
-              f"quadratic work ratio (B/{rows})^2 to the full batch, which itself needs 9 BxB fp32 matrices")
+    name = args.workload if args.workload in WORKLOADS else "north_star"
+    b, d, _ = WORKLOADS[name]
+    if b <= CPU_SAMPLE_ROWS:  # config 1: 5 warm-up + 30 timed iterations of the real shape (BASELINE.md section 4)
+        steps, warmup = max(args.steps, 30), max(args.warmup, 5)
+    else:
+        steps, warmup = args.steps, args.warmup
+    cpu, dt = cpu_block(b, d, steps, warmup)
     line = {
-        "impl": "reference", "metric": "contrastive_loss_fwd_bwd_samples_per_sec", "value": rate, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "impl": "reference", "metric": "contrastive_loss_fwd_bwd_samples_per_sec", "value": cpu["value"],
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cpu["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"tri-modal contrastive loss fwd+bwd, global batch {b}, dim {d}", "rows_global": b,
-                   "dim": d, "reference_sample_rows": rows},
-        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                   "dim": d, "reference_sample_rows": min(CPU_SAMPLE_ROWS, b), "extrapolated": cpu["extrapolated"]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -222,17 +251,72 @@ def stage_breakdown(run, steps):
                 continue
             acc.setdefault(name, []).append(a.elapsed_time(b))
     avg = {k: sum(v) / len(v) for k, v in acc.items()}
-    # the sharded path marks sub-stages (tile waves, the two GEMM roles, the statistics exchange): fold them into the
-    # six stage names, keeping the detail under "<stage>/<sub>"
-    folds = {"forward_tiles_local": "forward_tiles", "forward_tiles_wave1": "forward_tiles",
-             "forward_reduce": "forward_finish", "forward_barrier1": "forward_finish",
+    # the sharded path marks sub-stages (the two GEMM roles, the statistics exchange): fold them into the six stage
+    # names, keeping the detail under "<stage>/<sub>"
+    folds = {"forward_reduce": "forward_finish", "forward_barrier1": "forward_finish",
              "backward_gemms_col": "backward_gemms", "backward_gemms_row": "backward_gemms"}
     out = {}
     for k, v in avg.items():
-        tgt = "forward_tiles" if k.startswith("forward_tiles_") else folds.get(k, k)
+        tgt = folds.get(k, k)
         out[tgt] = out.get(tgt, 0.0) + v
         if tgt != k:
             out[f"{tgt}/{k}"] = v
+    return out
+
+
+def reference_tail_eager(img, txt, aud, scales):
+    """The reference's statements (model.py:247-272 with clip_loss / contrastive_loss, model.py:52-58) on whatever
+    device and dtype the tensors have -- what the unmodified reference runs under torch eager, fwd + bwd."""
+    import torch
+    import torch.nn.functional as F
+
+    for p in (img, txt, aud, *scales):
+        p.grad = None
+    img_n = img / img.norm(p=2, dim=-1, keepdim=True)
+    txt_n = txt / txt.norm(p=2, dim=-1, keepdim=True)
+    aud_n = aud / aud.norm(p=2, dim=-1, keepdim=True)
+    total = 0
+    for a, b, t in ((img_n, txt_n, scales[0]), (txt_n, aud_n, scales[1]), (aud_n, img_n, scales[2])):
+        sim = torch.matmul(a, b.t()) * t.exp()
+        labels = torch.arange(sim.shape[0], device=sim.device)
+        total = total + (F.cross_entropy(sim, labels) + F.cross_entropy(sim.t(), labels)) / 2.0
+    total.backward()
+    return total
+
+
+def gpu_eager_block(dev, shapes, ours_ms):
+    """`gpu_eager_baseline`: the reference's own tail under torch eager (cuBLAS + ATen kernels) on this GPU, fp32 (what
+    the reference runs) and bf16 (what it would run under autocast-style casting), CUDA events, 1 warm-up + 3 timed."""
+    import torch
+
+    out = {}
+    for name, (b, d) in shapes.items():
+        g = torch.Generator(device=dev).manual_seed(1234)
+        base = [torch.randn(b, d, device=dev, generator=g) for _ in range(3)]
+        entry = {"rows": b, "dim": d, "fused_ms": ours_ms.get(name)}
+        for label, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            try:
+                leaves = [x.to(dt).requires_grad_(True) for x in base]
+                scales = [torch.tensor(LOGIT_SCALE_INIT, device=dev, requires_grad=True) for _ in range(3)]
+                torch.cuda.reset_peak_memory_stats(dev)
+                reference_tail_eager(*leaves, scales)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    reference_tail_eager(*leaves, scales)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 3
+                entry[label] = {"ms_per_step": ms, "samples_per_s": b / (ms * 1e-3),
+                                "peak_gib": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                                "fused_speedup": (ms / ours_ms[name]) if ours_ms.get(name) else None}
+                del leaves, scales
+            except RuntimeError as e:  # out of memory at this shape
+                entry[label] = {"error": str(e).split("\n")[0][:160]}
+            torch.cuda.empty_cache()
+        out[name] = entry
+        del base
     return out
 
 
@@ -242,9 +326,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS) + ["sweep"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip configs 1 / 2 and the GPU-eager baseline")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: run the collectives on the compute stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -275,18 +359,19 @@ def main():
         pg = dist.group.WORLD
     peaks = load_peaks()
 
-    def make_inputs(b, d, shard):
+    def make_inputs(b, d, dtype, shard):
         g = torch.Generator(device=dev).manual_seed(1234)
-        full = [torch.randn(b, d, device=dev, generator=g).to(torch.bfloat16) for _ in range(3)]
+        full = [torch.randn(b, d, device=dev, generator=g).to(dtype) for _ in range(3)]
         if shard and world > 1:
             bl = b // world
             full = [f[rank * bl:(rank + 1) * bl].contiguous() for f in full]
         return full
 
-    def measure(b, d, shard, steps, warmup):
-        cfg = ops.TriContrastiveConfig(process_group=pg if shard else None, math="f16", grad_scale="ddp",
+    def measure(b, d, dt_name, shard, steps, warmup, with_e2e=True, with_stages=True):
+        dtype = torch.float32 if dt_name == "f32" else torch.bfloat16
+        cfg = ops.TriContrastiveConfig(process_group=pg if shard else None, math="auto", grad_scale="ddp",
                                        overlap=not args.no_overlap)
-        embs = make_inputs(b, d, shard)
+        embs = make_inputs(b, d, dtype, shard)
         t3 = torch.full((3,), LOGIT_SCALE_INIT, device=dev)
         g3 = torch.ones(3, device=dev)
         out = {}
@@ -306,7 +391,12 @@ def main():
         with sampler:
             ms = time_steps(resident_step, steps, 0, dist if shard else None)
         launches = counter() - launches0
-        stages = stage_breakdown(resident_step, min(steps, 5))
+        stages = stage_breakdown(resident_step, min(steps, 5)) if with_stages else {}
+        res = {"ms": ms, "stages": stages, "clocks": sampler.summary(), "launches": launches,
+               "loss": [float(x) for x in out["r"][0].tolist()], "rows_local": embs[0].shape[0]}
+        if not with_e2e:
+            ops._POOL.clear()
+            return res
 
         # end to end through the public autograd API with HOST buffers: every step copies its three embedding matrices
         # from pinned host memory and reads the three losses back.  Like a training loop with a prefetching loader, the
@@ -340,62 +430,103 @@ def main():
             torch.cuda.current_stream().synchronize()  # the caller reads the losses (main_pretraining.py:169-170)
             state["cur"] = 1 - slot
 
-        ms_e2e = time_steps(e2e_step, steps, warmup, dist if shard else None)
-        h2d = sum(h.numel() * h.element_size() for h in host)
+        res["ms_e2e"] = time_steps(e2e_step, steps, warmup, dist if shard else None)
+        res["h2d"] = sum(h.numel() * h.element_size() for h in host)
         if shard and dist is not None:
             lt = torch.tensor([launches], device=dev, dtype=torch.int64)
             dist.all_reduce(lt)
-            launches = int(lt.item())
-        return {"ms": ms, "ms_e2e": ms_e2e, "stages": stages, "clocks": sampler.summary(), "h2d": h2d,
-                "launches": launches,
-                "loss": [float(x) for x in out["r"][0].tolist()], "rows_local": embs[0].shape[0]}
+            res["launches"] = int(lt.item())
+        ops._POOL.clear()
+        return res
 
-    b, d = WORKLOADS[args.workload]
-    main_res = measure(b, d, True, args.steps, args.warmup)
+    if args.workload == "sweep":
+        return run_sweep(args, measure, world, rank, peaks, dist)
+
+    b, d, dt_name = WORKLOADS[args.workload]
+    shard = args.workload == "north_star"
+    if not shard and world > 1:
+        raise SystemExit("configs 1 and 2 are single-GPU workloads (BASELINE.json): run them with --gpus 1")
+    # The small BASELINE configs are measured FIRST, from an idle GPU: after a long run at the 1 kW power cap the SM
+    # clock stays low for a while (a sweep point measured right after a 128k batch ran at 832 MHz), which says nothing
+    # about a 1 ms workload.  Their clocks are recorded next to the numbers.
+    also_res = {}
+    if not args.no_also and rank == 0 and world == 1:
+        for name in ("cfg1", "cfg2"):
+            if name != args.workload:
+                b2, d2, dt2 = WORKLOADS[name]
+                also_res[name] = measure(b2, d2, dt2, False, max(args.steps, 20), args.warmup)
+    main_res = measure(b, d, dt_name, shard, args.steps, args.warmup)
     flops = 18.0 * b * b * d
     value = b / (main_res["ms"] * 1e-3)
     tflops_per_gpu = flops / world / (main_res["ms"] * 1e-3) / 1e12
+    st = main_res["stages"]
     # dominant kernel: the gradient GEMM launch (6 of the 9 contractions = 12 B^2 D / world flops per launch)
-    gemm_ms = main_res["stages"].get("backward_gemms")
+    gemm_ms = st.get("backward_gemms")
     gemm_tf = 12.0 * b * b * d / world / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
-    stage_tf = {}
-    for name, fl in (("forward_tiles", 6.0), ("backward_tiles", 6.0), ("backward_gemms", 12.0)):
-        if main_res["stages"].get(name):
-            stage_tf[name] = fl * b * b * d / world / (main_res["stages"][name] * 1e-3) / 1e12
+    stashed = dt_name == "bf16" and d >= 640
+    stage_rates = {}
+    if st.get("forward_tiles"):
+        stage_rates["forward_tiles_tflops"] = 6.0 * b * b * d / world / (st["forward_tiles"] * 1e-3) / 1e12
+    if gemm_tf:
+        stage_rates["backward_gemms_tflops"] = gemm_tf
+    if st.get("backward_tiles"):
+        if stashed:  # the in-place stash -> G' conversion executes no algorithmic flop: an HBM pass, 4 bytes per logit
+            gbs = 3.0 * 4.0 * b * b / world / (st["backward_tiles"] * 1e-3) / 1e9
+            stage_rates["backward_scale_gbs"] = gbs
+            stage_rates["backward_scale_frac_of_hbm_peak"] = gbs / peaks["hbm_gbs"]
+        else:        # the recompute backward executes 6 B^2 D flop that the algorithmic count does not include
+            stage_rates["backward_tiles_executed_tflops"] = 6.0 * b * b * d / world / (st["backward_tiles"] * 1e-3) / 1e12
 
-    also = None
-    if not args.no_also and args.workload == "north_star" and rank == 0 and world == 1:
-        b2, d2 = WORKLOADS["cfg2"]
-        r2 = measure(b2, d2, False, max(args.steps, 20), args.warmup)
-        also = {"cfg2_8192x512_bf16_1gpu": {
-            "value": b2 / (r2["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": r2["ms"],
-            "tflops_algorithmic": 18.0 * b2 * b2 * d2 / (r2["ms"] * 1e-3) / 1e12,
-            "frac_of_bf16_peak": 18.0 * b2 * b2 * d2 / (r2["ms"] * 1e-3) / 1e12 / peaks["bf16_tflops"],
-            "e2e_value": b2 / (r2["ms_e2e"] * 1e-3), "stages_ms": r2["stages"]}}
+    also, eager = None, None
+    if not args.no_also and rank == 0 and world == 1:
+        also = {}
+        ours_ms = {args.workload: main_res["ms"]}
+        for name in ("cfg2", "cfg1"):
+            if name == args.workload:
+                continue
+            b2, d2, dt2 = WORKLOADS[name]
+            r2 = also_res[name]
+            ours_ms[name] = r2["ms"]
+            tf2 = 18.0 * b2 * b2 * d2 / (r2["ms"] * 1e-3) / 1e12
+            also[f"{name}_{b2}x{d2}_{dt2}_1gpu"] = {
+                "value": b2 / (r2["ms"] * 1e-3), "unit": "samples/s", "ms_per_step": r2["ms"],
+                "tflops_algorithmic": tf2, "frac_of_bf16_peak": tf2 / peaks["bf16_tflops"],
+                "e2e_value": b2 / (r2["ms_e2e"] * 1e-3), "gpu_launches_per_step": r2["launches"] / max(args.steps, 20),
+                "clocks": r2["clocks"], "stages_ms": r2["stages"]}
+        shapes = {k: WORKLOADS[k][:2] for k in ours_ms}
+        eager = gpu_eager_block(dev, shapes, ours_ms)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows = min(CPU_SAMPLE_ROWS, b)
-        sub_rate, dt, threads = cpu_tail_rate(rows, d, steps=3, warmup=1)
-        cpu = {"value": cpu_full_batch_rate(rows, b, dt), "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"{rows}-row sub-batch of the {b}x{d} workload, fp32 torch CPU, 1 warm-up + 3 timed steps "
-                         f"({dt:.2f} s/step = {sub_rate:.0f} samples/s at B={rows}), scaled by the quadratic work "
-                         f"ratio (B/{rows})^2 to the full batch"}
+        if b <= CPU_SAMPLE_ROWS:
+            cpu, _ = cpu_block(b, d, 30, 5)
+        else:
+            cpu, _ = cpu_block(b, d, 3, 1)
+            if not args.no_also:  # config 1: the reference functions timed for real (5 + 30)
+                c1, _ = cpu_block(*WORKLOADS["cfg1"][:2], 30, 5)
+                cpu["cfg1_256x512_f32"] = c1
 
     if rank == 0:
+        tstep = load_traffic(b, d, world)
         line = {
             "metric": "contrastive_loss_fwd_bwd_samples_per_sec", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
-            "data": "synthetic",
-            "config": {"workload": f"tri-modal contrastive loss fwd+bwd, global batch {b}, dim {d}, bf16 embeddings "
-                                   f"in / bf16 gradients out, fp16 tensor-core operands with fp32 accumulation",
-                       "rows_global": b, "rows_per_gpu": main_res["rows_local"], "dim": d,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16" if dt_name == "bf16" else "f16x3", "data": "synthetic",
+            "config": {"workload": f"tri-modal contrastive loss fwd+bwd, global batch {b}, dim {d}, "
+                                   + ("bf16 embeddings in / bf16 gradients out, fp16 tensor-core operands with fp32 "
+                                      "accumulation" if dt_name == "bf16" else
+                                      "fp32 embeddings and gradients, split fp16 operands (3 tensor-core products per "
+                                      "contraction, fp32 parity mode)"),
+                       "name": args.workload, "rows_global": b, "rows_per_gpu": main_res["rows_local"], "dim": d,
                        "parallelism": f"row-strip dp{world}",
                        "l2": "no explicit flush: each step streams the 3 G' strips (2*B*B/world bytes each) through "
-                             "HBM, far larger than the 126 MB L2"},
+                             "HBM, far larger than the 126 MB L2" if b >= 8192 else
+                             "no explicit flush: this BASELINE config is smaller than L2 by definition"},
             "tflops_algorithmic_per_gpu": tflops_per_gpu,
             "frac_of_bf16_peak_per_gpu": tflops_per_gpu / peaks["bf16_tflops"],
+            "frac_of_bf16_sustained_peak_per_gpu": (tflops_per_gpu / peaks["bf16_tflops_sustained"])
+            if peaks.get("bf16_tflops_sustained") else None,
             "clocks": main_res["clocks"],
             "e2e": {"value": b / (main_res["ms_e2e"] * 1e-3), "unit": "samples/s", "ms_per_step": main_res["ms_e2e"],
                     "h2d_bytes_per_step": main_res["h2d"], "d2h_bytes_per_step": 12},
@@ -403,16 +534,65 @@ def main():
             "roofline": {"bound": "tensor", "kernel": "gemm_wide_kernel (backward_gemms)", "achieved": gemm_tf,
                          "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": (gemm_tf / peaks["bf16_tflops"]) if gemm_tf else None,
-                         "traffic": load_traffic(b, d, world),
+                         "traffic": tstep,
+                         "traffic_note": None if tstep is not None else
+                         "the committed ncu --set full capture (profiles/traffic.json) is of the 1-GPU north-star launch; "
+                         "no capture exists for this workload / world size (ncu is never run on multi-rank commands)",
                          "algorithmic_flops_per_launch": 12.0 * b * b * d / world,
                          "peak_source": peaks["source"] + ", burst figure",
-                         "stage_ms": main_res["stages"], "stage_tflops": stage_tf},
+                         "stage_ms": st, "stage_rates": stage_rates},
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
             "loss": main_res["loss"],
         }
         if also:
             line["also"] = also
         print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_sweep(args, measure, world, rank, peaks, dist):
+    """BASELINE config 5: global batch 4k-128k x dim 512/768/1024 at this world size.  One JSON line per point into
+    gpurun_out/sweep_w<N>.jsonl (copied to profiles/ by hand), one summary line on stdout."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    points = []
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, f"sweep_w{world}.jsonl")
+    f = open(path, "w") if rank == 0 else None
+    for b in SWEEP_B:  # small batches first; every point starts from a GPU that has idled for a moment (see main)
+        for d in SWEEP_D:
+            if b % (world * 256) != 0:
+                continue
+            time.sleep(0.5)
+            need = 3 * 2 * (b // world) * b + 40 * b * d  # the three fp16 G' strips + operands / gradients
+            if need > 0.8 * free:
+                continue
+            steps = 3 if b >= 65536 else 5
+            r = measure(b, d, "bf16", True, steps, 3, with_e2e=False, with_stages=False)
+            tf = 18.0 * b * b * d / world / (r["ms"] * 1e-3) / 1e12
+            pt = {"rows_global": b, "dim": d, "n_gpus": world, "ms_per_step": r["ms"], "samples_per_s": b / (r["ms"] * 1e-3),
+                  "tflops_algorithmic_per_gpu": tf, "frac_of_bf16_peak_per_gpu": tf / peaks["bf16_tflops"],
+                  "sm_mhz": r["clocks"].get("sm_mhz"), "loss": r["loss"][0]}
+            points.append(pt)
+            if f is not None:
+                f.write(json.dumps(pt) + "\n")
+                f.flush()
+    if f is not None:
+        f.close()
+        best = max(points, key=lambda p: p["frac_of_bf16_peak_per_gpu"]) if points else None
+        print(json.dumps({
+            "metric": "contrastive_loss_fwd_bwd_samples_per_sec", "value": best["samples_per_s"] if best else None,
+            "unit": "samples/s", "n_gpus": world, "steps": 5, "warmup": 3,
+            "ms_per_step": best["ms_per_step"] if best else None, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "BASELINE config 5: global-batch sweep 4k-128k x dim 512/768/1024 (value = the best point)",
+                       "points_file": os.path.relpath(path, ROOT)},
+            "sweep": points}), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

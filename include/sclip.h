@@ -97,7 +97,8 @@ typedef struct sclip_layout {
   uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed);
                              cleared by sclip_prologue, read back by sclip_read_status                            */
   uint64_t rowterm_part;  /* [3][ceil(rows_local/64)] fp64 partial sums of the row term of the loss
-                             [read by the peers in sclip_forward_loss_peers]                                      */
+                             [read by the peers in sclip_forward_loss_peers], followed by
+                             [3][ceil(rows_global/1024)] fp64 partial sums of its column term                     */
   uint64_t sync;          /* [64] int32 flags and counters that live across calls (per-source-rank "shard landed"
                              epochs, block counters).  THE OWNER ZEROES THIS AREA ONCE when the workspace is
                              allocated; the library never needs it cleared again.                                 */

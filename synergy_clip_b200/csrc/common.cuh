@@ -117,6 +117,7 @@ struct Workspace {  // resolved device pointers of one workspace blob
 constexpr int kSyncLanded = 0;       // [SCLIP_MAX_PEERS] epoch of the last complete shard per source rank
 constexpr int kSyncArrived = 16;     // [SCLIP_MAX_PEERS] block counters of sclip_pull_shards
 constexpr int kSyncFinishDone = 32;  // block counter of sclip_backward_finish
+constexpr int kSyncLossDone = 33;    // [3] block counters of the loss kernel
 constexpr int kSyncWords = 64;
 
 struct FwdParams {
@@ -198,6 +199,7 @@ int staging_slabs(int ew, bool split);  // 16 KiB G' staging slabs the backward 
 // t3_for_diag != null: also write this rank's positive-pair logits into diag_all (stash forward)
 int launch_prologue(const Workspace& w, const void* const x3[3], const float* t3_for_diag, cudaStream_t stream);
 int reduce_row_blocks(const sclip_problem& pb);  // entries per pair of rowterm_part
+int loss_col_chunks(const sclip_problem& pb);    // entries per pair of the column-term partial sums behind it
 int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream);
 // col_lse_all: the ranks' statistics gathered by a collective; peer_ws: read them from the peers' workspaces (and
 // compute the complete losses); both null: world == 1

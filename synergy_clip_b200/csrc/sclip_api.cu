@@ -178,7 +178,7 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->fac_col = take(3 * 2 * align_up(bg, 64) * 4);
   lay->dot_part = take(3 * ((bl + 7) / 8) * 4);
   lay->status = take(4 * 4);
-  lay->rowterm_part = take(3 * static_cast<uint64_t>(reduce_row_blocks(*pb)) * 8);
+  lay->rowterm_part = take(3 * static_cast<uint64_t>(reduce_row_blocks(*pb) + loss_col_chunks(*pb)) * 8);
   lay->sync = take(kSyncWords * 4);
   lay->total_bytes = off;
   return SCLIP_OK;

@@ -329,6 +329,8 @@ struct LossArgs {
   const uint8_t* peer[SCLIP_MAX_PEERS];  // peer mode: workspace bases in rank order (peer[0] == null: share mode)
   unsigned long long lse_col_local_off, rowterm_off;
   const double* rowterm_part;
+  double* colterm_part;  // [3][column chunks] per-block sums of the column term
+  unsigned int* done;    // [3] block counters (zero between launches)
   const float* col_sum_local;
   float* lse_col;
   float* col_inv;
@@ -341,13 +343,19 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {  // peer data:
   return __ldcg(p);
 }
 
-__global__ void __launch_bounds__(1024) forward_loss_kernel(const LossArgs a) {
+// grid (column chunks of kLossCols, 3 pairs); one column per thread, so a rank's NVLink loads of all peers' statistics are
+// in flight at once (the first version walked 32 columns per thread one after the other: 0.24 ms at 4 ranks).  The
+// per-block column terms go to colterm_part and the last block to finish a pair adds everything up in a fixed order.
+constexpr int kLossCols = 1024;
+
+__global__ void __launch_bounds__(kLossCols) forward_loss_kernel(const LossArgs a) {
   __shared__ double red[32];
-  const int p = blockIdx.x;
+  __shared__ bool last;
+  const int p = blockIdx.y;
   const bool peers = a.peer[0] != nullptr;
-  float* lse_col = a.lse_col + static_cast<size_t>(p) * a.rows_global;
+  const int j = blockIdx.x * kLossCols + threadIdx.x;
   double acc = 0.0;
-  for (int j = threadIdx.x; j < a.rows_global; j += blockDim.x) {
+  if (j < a.rows_global) {
     float v;
     if (!peers && a.col_lse_all == nullptr) {
       v = a.lse_col_local[static_cast<size_t>(p) * a.rows_global + j];
@@ -371,25 +379,45 @@ __global__ void __launch_bounds__(1024) forward_loss_kernel(const LossArgs a) {
       v = mx + logf(sum);
       a.col_inv[static_cast<size_t>(p) * a.rows_global + j] = expf(-v);
     }
-    lse_col[j] = v;
+    a.lse_col[static_cast<size_t>(p) * a.rows_global + j] = v;
     // column term: every column in peer mode, the columns of this rank's own rows otherwise
-    if (peers || (j >= a.row_offset && j < a.row_offset + a.rows_local)) acc += static_cast<double>(v);
-  }
-  // row term: sum_i (lse_row_i - 2 L_ii) from the per-block partial sums of forward_reduce_kernel
-  if (peers) {
-    for (int w = 0; w < a.world; ++w) {
-      const double* rt = reinterpret_cast<const double*>(a.peer[w] + a.rowterm_off) + static_cast<size_t>(p) * a.row_blocks;
-      for (int i = threadIdx.x; i < a.row_blocks; i += blockDim.x) acc += __ldcg(rt + i);
-    }
-  } else {
-    for (int i = threadIdx.x; i < a.row_blocks; i += blockDim.x)
-      acc += a.rowterm_part[static_cast<size_t>(p) * a.row_blocks + i];
+    if (peers || (j >= a.row_offset && j < a.row_offset + a.rows_local)) acc = static_cast<double>(v);
   }
   acc = warp_sum_d(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
-    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    double v = red[threadIdx.x];
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) {
+      a.colterm_part[static_cast<size_t>(p) * gridDim.x + blockIdx.x] = v;
+      __threadfence();
+      last = atomicAdd(a.done + p, 1u) == gridDim.x - 1;
+      if (last) a.done[p] = 0u;
+    }
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // the last block of this pair: column terms of all blocks + row terms sum_i (lse_row_i - 2 L_ii) (per-block partial
+  // sums of forward_reduce_kernel; in peer mode those of every rank, read from the peers)
+  double tot = 0.0;
+  for (int i = threadIdx.x; i < static_cast<int>(gridDim.x); i += blockDim.x)
+    tot += __ldcg(a.colterm_part + static_cast<size_t>(p) * gridDim.x + i);
+  if (peers) {
+    for (int w = 0; w < a.world; ++w) {
+      const double* rt = reinterpret_cast<const double*>(a.peer[w] + a.rowterm_off) + static_cast<size_t>(p) * a.row_blocks;
+      for (int i = threadIdx.x; i < a.row_blocks; i += blockDim.x) tot += __ldcg(rt + i);
+    }
+  } else {
+    for (int i = threadIdx.x; i < a.row_blocks; i += blockDim.x)
+      tot += a.rowterm_part[static_cast<size_t>(p) * a.row_blocks + i];
+  }
+  tot = warp_sum_d(tot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = red[threadIdx.x];
     v = warp_sum_d(v);
     if (threadIdx.x == 0) {
       const float loss = static_cast<float>(v / (2.0 * a.rows_global));
@@ -816,6 +844,7 @@ int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __
 }
 
 int reduce_row_blocks(const sclip_problem& pb) { return (pb.rows_local + kReduceRows - 1) / kReduceRows; }
+int loss_col_chunks(const sclip_problem& pb) { return (pb.rows_global + kLossCols - 1) / kLossCols; }
 
 int launch_forward_reduce(const Workspace& w, int row_tiles_done, cudaStream_t stream) {
   const int rb = reduce_row_blocks(w.pb), cb = (w.pb.rows_global + kReduceRows - 1) / kReduceRows;
@@ -838,6 +867,8 @@ int launch_forward_loss(const Workspace& w, const float* col_lse_all, const void
   a.lse_col_local_off = w.lay.lse_col_local;
   a.rowterm_off = w.lay.rowterm_part;
   a.rowterm_part = w.rowterm_part;
+  a.colterm_part = w.rowterm_part + 3 * static_cast<size_t>(reduce_row_blocks(w.pb));
+  a.done = reinterpret_cast<unsigned int*>(w.sync) + kSyncLossDone;
   a.col_sum_local = w.col_sum_local;
   a.lse_col = w.lse_col;
   a.col_inv = w.col_inv;
@@ -848,7 +879,7 @@ int launch_forward_loss(const Workspace& w, const float* col_lse_all, const void
   a.row_offset = w.pb.row_offset;
   a.world = w.pb.world;
   a.row_blocks = reduce_row_blocks(w.pb);
-  forward_loss_kernel<<<3, 1024, 0, stream>>>(a);
+  forward_loss_kernel<<<dim3(loss_col_chunks(w.pb), 3), kLossCols, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }

@@ -83,3 +83,41 @@ def test_ranks_match_global_batch_oracle(tmp_path, rows_local, dim, dtype_name, 
         assert err < tol, (key, err)
     dscale = np.mean([r["dscale"] for r in ranks], axis=0) if grad_scale == "ddp" else ranks[0]["dscale"]
     assert np.max(np.abs(dscale - want["dscale"])) / np.max(np.abs(want["dscale"])) < tol
+
+
+def _worker_no_set_device(rank, world, rows, dim, out_dir):
+    """What the reference driver does: mp.spawn, `.to(rank)`, NO torch.cuda.set_device (main_pretraining.py:64,137-138,
+    285-293) -- on every rank > 0 the current device stays 0 while the embeddings live on cuda:rank."""
+    from synergy_clip_b200 import fused_tri_contrastive
+
+    assert torch.cuda.current_device() == 0
+    dev = torch.device("cuda", rank)
+    embs = closed_form.synthetic_embeddings(rows, dim, 500 + rank, 0.2)
+    leaves = [torch.from_numpy(e).to(dev).requires_grad_(True) for e in embs]
+    ts = [torch.tensor(t, device=dev, requires_grad=True) for t in T3]
+    losses = fused_tri_contrastive(*leaves, *ts)  # local batch, like the reference (no process group)
+    sum(w * l for w, l in zip(W3, losses)).backward()
+    with torch.no_grad():  # evaluation path and the scorers on the same device
+        again = fused_tri_contrastive(*leaves, *ts)
+    assert torch.cuda.current_device() == 0  # the op must not leak a device switch either
+    np.savez(os.path.join(out_dir, f"nd{rank}.npz"), loss=np.array([l.item() for l in losses]),
+             loss_eval=np.array([l.item() for l in again]), dimg=leaves[0].grad.double().cpu().numpy(),
+             dscale=np.array([t.grad.item() for t in ts]))
+
+
+def test_ranks_that_never_call_set_device(tmp_path):
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rows, dim = 300, 256
+    mp.spawn(_worker_no_set_device, args=(world, rows, dim, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        embs = closed_form.synthetic_embeddings(rows, dim, 500 + r, 0.2)
+        want = closed_form.tri_contrastive(*embs, T3, W3)
+        got = dict(np.load(tmp_path / f"nd{r}.npz"))
+        assert np.max(np.abs(got["loss"] - want["loss"]) / want["loss"]) < 1e-5
+        assert np.max(np.abs(got["loss_eval"] - want["loss"]) / want["loss"]) < 1e-5
+        assert np.sqrt(((got["dimg"] - want["dimg"]) ** 2).sum() / (want["dimg"] ** 2).sum()) < 1e-5
+        assert np.max(np.abs(got["dscale"] - want["dscale"])) / np.max(np.abs(want["dscale"])) < 1e-5

@@ -60,7 +60,9 @@ typedef struct sclip_problem {
   int32_t dtype;       /* sclip_dtype of img/txt/aud and of dimg/dtxt/daud    */
   int32_t math;        /* sclip_math                                          */
   int32_t world;       /* number of ranks sharing the global batch (>= 1)     */
-  int32_t reserved;
+  int32_t parity;      /* 0 | 1: which copy of the exchange buffers (xhat, diag_all) this step uses.  With
+                          sclip_push_shards a rank writes its shard straight into the peers' workspaces without
+                          waiting for them, so consecutive steps must alternate; otherwise 0 (world == 1: 0)  */
 } sclip_problem;
 
 /* Byte offsets into the workspace blob.  Buffers marked [exchange] are the ones the host moves
@@ -68,7 +70,8 @@ typedef struct sclip_problem {
 typedef struct sclip_layout {
   uint64_t total_bytes;
   uint64_t xhat;          /* [3][rows_global][dim] fp16 normalised embeddings; this rank's rows are written by
-                             sclip_prologue at row_offset [exchange: all-gather of the row shards]           */
+                             sclip_prologue at row_offset [exchange: all-gather of the row shards].  world > 1:
+                             two copies; the offset reported here is that of problem->parity               */
   uint64_t xhat_lo;       /* same shape, low halves (SCLIP_MATH_F16X3 only, else == xhat)                    */
   uint64_t inv_norm;      /* [3][rows_local] fp32                                                            */
   uint64_t row_part;      /* [3][col_tiles][2][rows_local] fp32 partial row sums (per 128-column slice)      */
@@ -100,7 +103,7 @@ typedef struct sclip_layout {
                              [read by the peers in sclip_forward_loss_peers], followed by
                              [3][ceil(rows_global/1024)] fp64 partial sums of its column term                     */
   uint64_t sync;          /* [64] int32 flags and counters that live across calls (per-source-rank "shard landed"
-                             epochs, block counters).  THE OWNER ZEROES THIS AREA ONCE when the workspace is
+                             epochs -- written by the peers --, block counters).  THE OWNER ZEROES THIS AREA ONCE when the workspace is
                              allocated; the library never needs it cleared again.                                 */
   int32_t row_tiles;      /* ceil(rows_local / 128)   */
   int32_t col_tiles;      /* ceil(rows_global / 256)  */
@@ -143,11 +146,11 @@ int sclip_forward_tiles(const sclip_problem* problem, void* ws, const float* t3,
  * ranks' columns that wraps around the end of the global batch); col_tile_end - col_tile_begin <= col_tiles. */
 #define SCLIP_FWD_WRAP 2
 /* flags & SCLIP_FWD_WAIT_PEERS (world > 1, rows_local a multiple of 256, the full column range): ONE launch covers
- * every column; the tiles are taken rank by rank -- this rank's own columns first, then those of rank + 1, rank + 2,
- * ... -- and the kernel itself waits (acquire loads of the per-rank "landed" flags in `sync`) until
- * sclip_pull_shards(..., epoch) has completed a rank's shard before touching its columns.  The pulls run concurrently
- * on another stream; give them SMs with max_sms.  `epoch` must be the value passed to that sclip_pull_shards call
- * (use a counter that grows by one per forward). */
+ * every column; the tiles are taken rank by rank -- this rank's own columns first, then those of rank - 1, rank - 2,
+ * ... (the order in which the pushes of the peers land here) -- and the kernel itself waits (acquire loads of the per-rank "landed" flags in `sync`) until the rank that owns
+ * a shard has pushed it (sclip_push_shards(..., epoch) on that rank) before touching its columns.  The pushes run
+ * concurrently on another stream; give them SMs with max_sms.  `epoch` must be the value every rank passes to
+ * sclip_push_shards in this step (a counter that grows by one per forward). */
 #define SCLIP_FWD_WAIT_PEERS 4
 /* max_sms > 0: the persistent grid takes at most that many SMs, leaving the rest to concurrently running
  * communication kernels (0 = all). */
@@ -231,14 +234,19 @@ int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, in
  * the same stream before each call: the sources must be complete and must not be rewritten while peers read). */
 #define SCLIP_MAX_PEERS 16
 
-/* Pull all-gather: copy the normalised operand shards (and their positive-pair logits) of the `count` ranks
- * (rank + first + i) % world, i in [0, count), into this rank's xhat / diag_all.  At most max_blocks thread blocks of
- * block_threads (<= 1024) threads: either big blocks on SMs left free by max_sms, or 256-thread blocks, one
- * per SM, which fit beside a resident persistent tile CTA.
- * The shards complete one after the other in that order; when a shard is complete the kernel publishes
- * landed[source rank] = epoch in `sync` (release), which forward tiles launched with SCLIP_FWD_WAIT_PEERS acquire. */
-int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
-                      int max_blocks, int block_threads, int epoch, void* stream);
+/* Push all-gather: write this rank's normalised operand shard (and its positive-pair logits) into the xhat / diag_all
+ * of every other rank, rank + 1 first, then rank + 2, ... -- every rank does the same, so at any moment every rank
+ * receives from exactly one peer -- and, as each destination is complete, publish landed[this rank] = epoch in the
+ * DESTINATION's `sync` area (system-scope release), which that rank's forward tiles launched with
+ * SCLIP_FWD_WAIT_PEERS acquire.  No barrier is needed before the call: the exchange buffers exist twice
+ * (problem->parity, alternate it every step), and a peer that is still one step behind reads the other copy.
+ * At most max_blocks thread blocks of block_threads (<= 1024) threads, on the SMs the tile kernel leaves free (max_sms). */
+int sclip_push_shards(const sclip_problem* problem, void* ws, void* const* peer_ws, int max_blocks, int block_threads,
+                      int epoch, void* stream);
+
+/* A one-block kernel that completes once every other rank's shard of this epoch has landed in this workspace: for
+ * forward launches that do not wait themselves (SCLIP_FWD_WAIT_PEERS needs shards that are multiples of 256 rows). */
+int sclip_wait_shards(const sclip_problem* problem, void* ws, int epoch, void* stream);
 
 /* Pull reduce-scatter: col_contrib[m][i][:] = sum over ranks r (rank order) of rank r's dxhat_col[m][row_offset + i][:]
  * -- the column-role gradients of this rank's rows, ready for sclip_backward_finish. */

@@ -25,7 +25,7 @@ class Problem(Structure):
         ("dtype", c_int32),
         ("math", c_int32),
         ("world", c_int32),
-        ("reserved", c_int32),
+        ("parity", c_int32),
     ]
 
 
@@ -62,7 +62,8 @@ _PROTOTYPES = {
                               c_void_p]),
     "sclip_backward": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "sclip_pull_shards": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sclip_push_shards": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "sclip_wait_shards": (c_int, [POINTER(Problem), c_void_p, c_int, c_void_p]),
     "sclip_forward_loss_peers": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_void_p, c_void_p]),
     "sclip_read_status": (c_int, [POINTER(Problem), c_void_p, POINTER(c_int32), c_void_p]),
     "sclip_pull_reduce_cols": (c_int, [POINTER(Problem), c_void_p, c_void_p, c_int, c_int, c_void_p]),

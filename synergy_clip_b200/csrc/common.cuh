@@ -114,8 +114,8 @@ struct Workspace {  // resolved device pointers of one workspace blob
 };
 
 // slots of the `sync` area (32-bit words)
-constexpr int kSyncLanded = 0;       // [SCLIP_MAX_PEERS] epoch of the last complete shard per source rank
-constexpr int kSyncArrived = 16;     // [SCLIP_MAX_PEERS] block counters of sclip_pull_shards
+constexpr int kSyncLanded = 0;       // [SCLIP_MAX_PEERS] epoch of the last complete shard per source rank (peers write)
+constexpr int kSyncArrived = 16;     // [SCLIP_MAX_PEERS] block counters of sclip_push_shards (per destination)
 constexpr int kSyncFinishDone = 32;  // block counter of sclip_backward_finish
 constexpr int kSyncLossDone = 33;    // [3] block counters of the loss kernel
 constexpr int kSyncWords = 64;
@@ -213,8 +213,9 @@ int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream);
 int launch_normalise(const void* x, int dtype, int rows, int dim, __half* hi, __half* lo, float* inv_norm, bool split,
                      cudaStream_t stream);
 // peer-memory exchanges (world > 1, workspaces in symmetric memory); peer_ws[r] = base of rank r's workspace
-int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
-                       int block_threads, int epoch, cudaStream_t stream);
+int launch_push_shards(const Workspace& w, void* const* peer_ws, int max_blocks, int block_threads, int epoch,
+                       cudaStream_t stream);
+int launch_wait_shards(const Workspace& w, int epoch, cudaStream_t stream);
 int launch_pull_reduce(const Workspace& w, const void* const* peer_ws, int max_blocks, int block_threads,
                        cudaStream_t stream);
 int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream);

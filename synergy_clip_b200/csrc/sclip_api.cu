@@ -126,6 +126,10 @@ int check_problem(const sclip_problem* pb) {
     set_error("math=%d is neither SCLIP_MATH_F16 nor SCLIP_MATH_F16X3", pb->math);
     return SCLIP_ERR_ARGUMENT;
   }
+  if (pb->parity != 0 && (pb->parity != 1 || pb->world == 1)) {
+    set_error("parity=%d must be 0 or 1 (and 0 when world == 1)", pb->parity);
+    return SCLIP_ERR_ARGUMENT;
+  }
   if (pb->world < 1 || (pb->world == 1 && pb->rows_local != pb->rows_global)) {
     set_error("world=%d inconsistent with rows_local=%d rows_global=%d", pb->world, pb->rows_local, pb->rows_global);
     return SCLIP_ERR_ARGUMENT;
@@ -153,8 +157,10 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
     off = align_up(off + bytes, 256);
     return at;
   };
-  lay->xhat = take(3 * bg * d * 2);
-  lay->xhat_lo = x3 ? take(3 * bg * d * 2) : lay->xhat;
+  // world > 1: the exchange buffers exist twice (problem->parity picks the copy, see sclip_push_shards)
+  const uint64_t copies = pb->world > 1 ? 2 : 1, par = pb->world > 1 ? static_cast<uint64_t>(pb->parity) : 0;
+  lay->xhat = take(copies * 3 * bg * d * 2) + par * 3 * bg * d * 2;
+  lay->xhat_lo = x3 ? take(copies * 3 * bg * d * 2) + par * 3 * bg * d * 2 : lay->xhat;
   lay->inv_norm = take(3 * bl * 4);
   lay->row_part = take(3 * 2 * ntj * bl * 4);
   lay->col_part = take(3 * nti * bg * 4);
@@ -173,7 +179,7 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->dxhat_row = take(3 * bl * d * 4);
   lay->dxhat_col = pb->world > 1 ? take(3 * bg * d * 4) : lay->dxhat_row;
   lay->col_contrib = pb->world > 1 ? take(3 * bl * d * 4) : lay->dxhat_row;
-  lay->diag_all = take(3 * bg * 4);
+  lay->diag_all = take(copies * 3 * bg * 4) + par * 3 * bg * 4;
   lay->fac_row = take(3 * 2 * align_up(bl, 64) * 4);
   lay->fac_col = take(3 * 2 * align_up(bg, 64) * 4);
   lay->dot_part = take(3 * ((bl + 7) / 8) * 4);
@@ -828,19 +834,25 @@ static bool bad_block(int block_threads, int limit) {
   return true;
 }
 
-int sclip_pull_shards(const sclip_problem* problem, void* ws, const void* const* peer_ws, int first, int count,
-                      int max_blocks, int block_threads, int epoch, void* stream) {
+int sclip_push_shards(const sclip_problem* problem, void* ws, void* const* peer_ws, int max_blocks, int block_threads,
+                      int epoch, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (!rc) rc = check_peers(w, ws, peer_ws);
   if (rc) return rc;
-  if (first < 1 || count < 0 || first + count > w.pb.world) {
-    set_error("bad peer range first=%d count=%d (world %d)", first, count, w.pb.world);
+  if (bad_block(block_threads, 1024)) return SCLIP_ERR_ARGUMENT;
+  return launch_push_shards(w, peer_ws, max_blocks, block_threads, epoch, static_cast<cudaStream_t>(stream));
+}
+
+int sclip_wait_shards(const sclip_problem* problem, void* ws, int epoch, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (w.pb.world < 2 || w.pb.world > SCLIP_MAX_PEERS || w.pb.rows_local * w.pb.world != w.pb.rows_global) {
+    set_error("sclip_wait_shards needs 2 <= world <= %d equal row shards", SCLIP_MAX_PEERS);
     return SCLIP_ERR_ARGUMENT;
   }
-  if (bad_block(block_threads, 1024)) return SCLIP_ERR_ARGUMENT;
-  if (count == 0) return SCLIP_OK;
-  return launch_pull_shards(w, peer_ws, first, count, max_blocks, block_threads, epoch, static_cast<cudaStream_t>(stream));
+  return launch_wait_shards(w, epoch, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_loss_peers(const sclip_problem* problem, void* ws, const void* const* peer_ws, float* loss3,

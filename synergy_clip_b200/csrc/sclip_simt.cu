@@ -640,17 +640,78 @@ struct ScaleArgs {
   int row_offset;
 };
 
+// packed fp32 pairs (FFMA2 / FMUL2): half the floating-point instructions of the scalar form -- at the clock the power
+// cap leaves after the tile kernels (about 1.2 GHz) the scalar version of this pass was bound by instruction issue, not
+// by HBM (5.8 TB/s alone at 1.95 GHz, 4.9 TB/s inside the step)
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long x, unsigned long long y, unsigned long long z) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(x), "l"(y), "l"(z));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long x, unsigned long long y) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(y));
+  return d;
+}
+
+// DIAG: the block's 16 rows x 2048 columns contain positive pairs (one block in 2048 at the north-star shape); the
+// other blocks run the loop without the per-row test, which keeps four rows of loads in flight.
+template <bool DIAG>
+__device__ __forceinline__ void scale_rows(__half* ptr, size_t ld, const float* fr1, const float* fr2, int nrows,
+                                           const unsigned long long (&c1)[4], const unsigned long long (&c2)[4], int d0,
+                                           float kcp) {
+  constexpr int kBatch = 4;  // rows loaded before the first is stored (the pass is in place: the compiler must not be
+                             // left to order a row's load behind the previous row's store)
+  for (int r0 = 0; r0 < nrows; r0 += kBatch) {
+    uint4 raw[kBatch];
+    float r1[kBatch], r2[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int r = min(r0 + j, nrows - 1);
+      raw[j] = *reinterpret_cast<const uint4*>(ptr + static_cast<size_t>(r) * ld);
+      r1[j] = __ldg(fr1 + r);
+      r2[j] = __ldg(fr2 + r);
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const int r = r0 + j;
+      if (r >= nrows) break;
+      const unsigned long long r1p = pk2(r1[j], r1[j]), r2p = pk2(r2[j], r2[j]);
+      const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        const unsigned long long v = mul2(pk2(e.x, e.y), fma2(r1p, c1[k], mul2(r2p, c2[k])));
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+        if constexpr (DIAG) {  // the identity term, in fp32 before the rounding to fp16
+          if (d0 + r == 2 * k) lo -= kcp;
+          if (d0 + r == 2 * k + 1) hi -= kcp;
+        }
+        const __half2 hh = __floats2half2_rn(lo, hi);
+        o[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(ptr + static_cast<size_t>(r) * ld) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) {
   const int p = blockIdx.z;
   const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= a.rows_global) return;
-  float c1[8], c2[8];
-  const float* fc = a.fac_col + static_cast<size_t>(p) * 2 * a.ld_col;
+  unsigned long long c1[4], c2[4];  // column factors of this thread's 8 columns, as pairs
+  const float* fc = a.fac_col + static_cast<size_t>(p) * 2 * a.ld_col;  // (padded to 64 and zero-filled: no bound checks)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const bool ok = col + k < a.rows_global;
-    c1[k] = ok ? fc[col + k] : 0.f;
-    c2[k] = ok ? fc[a.ld_col + col + k] : 0.f;
+  for (int k = 0; k < 4; ++k) {
+    c1[k] = pk2(fc[col + 2 * k], fc[col + 2 * k + 1]);
+    c2[k] = pk2(fc[a.ld_col + col + 2 * k], fc[a.ld_col + col + 2 * k + 1]);
   }
   const float* fr = a.fac_row + static_cast<size_t>(p) * 2 * a.ld_row;
   const int row0 = blockIdx.y * kScaleRows;
@@ -662,22 +723,14 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
 #pragma unroll
   for (int r = 0; r < 3; ++r) mxsg = fmaxf(mxsg, fabsf(expf(a.t3[r]) * a.g3[r]));
   const float kcp = mxsg > 0.f ? kKappa * expf(a.t3[p]) * a.g3[p] / mxsg : 0.f;
-#pragma unroll 4
-  for (int r = 0; r < kScaleRows; ++r) {
-    const int row = row0 + r;
-    if (row >= a.rows_local) break;
-    const float r1 = fr[row], r2 = fr[a.ld_row + row];
-    __half* ptr = a.g + (static_cast<size_t>(p) * a.rows_local + row) * a.ld + col;
-    float v[8];
-    load8(ptr, v);
-    const int dcol = a.row_offset + row - col;  // position of the positive pair inside this thread's 8 columns
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] *= fmaf(r1, c1[k], r2 * c2[k]);
-      if (k == dcol) v[k] -= kcp;
-    }
-    *reinterpret_cast<uint4*>(ptr) = pack8_half(v);
-  }
+  const int nrows = min(kScaleRows, a.rows_local - row0);
+  __half* ptr = a.g + (static_cast<size_t>(p) * a.rows_local + row0) * a.ld + col;
+  const int d0 = a.row_offset + row0 - col;  // row r holds the positive pair at column offset d0 + r of this thread
+  const int g0 = a.row_offset + row0, bc0 = blockIdx.x * 2048;  // block-uniform: does the diagonal cross this block?
+  if (g0 + kScaleRows > bc0 && g0 < bc0 + 2048)
+    scale_rows<true>(ptr, a.ld, fr + row0, fr + a.ld_row + row0, nrows, c1, c2, d0, kcp);
+  else
+    scale_rows<false>(ptr, a.ld, fr + row0, fr + a.ld_row + row0, nrows, c1, c2, d0, kcp);
 }
 
 // ------------------------------------------------------------------------------------------------ peer memory
@@ -688,65 +741,83 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
 // signal-pad barriers on the same stream.
 __device__ __forceinline__ uint4 ld_peer(const uint4* p) { return __ldcg(p); }  // L2 only: never a stale L1 line
 
-struct PullShardArgs {
-  const uint8_t* peer[SCLIP_MAX_PEERS];   // workspace bases of the selected source ranks, in pull order
+struct PushShardArgs {
+  uint8_t* peer[SCLIP_MAX_PEERS];   // workspace bases of the destination ranks, in push order
   int peer_rank[SCLIP_MAX_PEERS];
   int count;
-  uint8_t* local;
-  unsigned long long xhat_off, xhat_lo_off, diag_off;
+  const uint8_t* local;
+  unsigned long long xhat_off, xhat_lo_off, diag_off, sync_off;
   int nseg;  // 3, or 6 with the low halves
-  int rows_local, rows_global, dim;
-  int* landed;            // [SCLIP_MAX_PEERS] per source rank: epoch of the last shard that is complete in this workspace
-  unsigned int* arrived;  // [SCLIP_MAX_PEERS] block counters (zero between launches)
+  int rows_local, rows_global, dim, rank;
+  unsigned int* arrived;  // [SCLIP_MAX_PEERS] block counters of this launch, per destination (zero between launches)
   int epoch;
 };
 
-// Every block walks the source ranks in the same order and copies its slice of each shard, so the shards complete one
-// after the other (the tile kernel consumes them in that order).  The last block to finish a shard publishes
-// landed[rank] = epoch with release semantics; forward tiles launched with SCLIP_FWD_WAIT_PEERS acquire it.
-__global__ void __launch_bounds__(1024) pull_shards_kernel(const PullShardArgs a) {
+// This rank's shard (its rows of the three normalised operand matrices, and their positive-pair logits) written into
+// every peer's workspace at the same offsets.  Every block walks the destinations in the same order and copies its
+// slice to each, so the destinations complete one after the other; the last block to finish a destination publishes
+// landed[this rank] = epoch in the DESTINATION's sync area with a system-scope release (the peers' forward tiles,
+// launched with SCLIP_FWD_WAIT_PEERS, acquire it).  Local loads, posted NVLink stores.
+__global__ void __launch_bounds__(1024) push_shards_kernel(const PushShardArgs a) {
   const size_t seg_units = static_cast<size_t>(a.rows_local) * a.dim * 2 / 16;  // 16-byte units per modality shard
   const size_t total = a.nseg * seg_units;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t row0 = static_cast<size_t>(a.rank) * a.rows_local;
+  auto locate = [&](size_t u) {
+    const int sg = static_cast<int>(u / seg_units);
+    const size_t w = u - sg * seg_units;
+    return (sg < 3 ? a.xhat_off : a.xhat_lo_off) + ((static_cast<size_t>(sg % 3) * a.rows_global + row0) * a.dim) * 2 + w * 16;
+  };
   for (int pi = 0; pi < a.count; ++pi) {
-    const uint8_t* src = a.peer[pi];
-    const size_t row0 = static_cast<size_t>(a.peer_rank[pi]) * a.rows_local;
-    auto locate = [&](size_t u) {
-      const int sg = static_cast<int>(u / seg_units);
-      const size_t w = u - sg * seg_units;
-      return (sg < 3 ? a.xhat_off : a.xhat_lo_off) + ((static_cast<size_t>(sg % 3) * a.rows_global + row0) * a.dim) * 2 +
-             w * 16;
-    };
+    uint8_t* dst = a.peer[pi];
     size_t u = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    for (; u + 3 * stride < total; u += 4 * stride) {  // four independent 16-byte loads in flight per thread
+    for (; u + 3 * stride < total; u += 4 * stride) {
       size_t o[4];
       uint4 v[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = locate(u + k * stride);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = ld_peer(reinterpret_cast<const uint4*>(src + o[k]));
+      for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const uint4*>(a.local + o[k]);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(a.local + o[k]) = v[k];
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(dst + o[k]) = v[k];
     }
     for (; u < total; u += stride) {
       const size_t o = locate(u);
-      *reinterpret_cast<uint4*>(a.local + o) = ld_peer(reinterpret_cast<const uint4*>(src + o));
+      *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(a.local + o);
     }
-    // positive-pair logits of the peer's rows (stash scaling)
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < 3u * a.rows_local; i += stride) {
       const size_t p = i / a.rows_local, r = i - p * a.rows_local;
       const size_t o = a.diag_off + (p * a.rows_global + row0 + r) * 4;
-      *reinterpret_cast<float*>(a.local + o) = __ldcg(reinterpret_cast<const float*>(src + o));
+      *reinterpret_cast<float*>(dst + o) = *reinterpret_cast<const float*>(a.local + o);
     }
-    __threadfence();
+    __threadfence_system();  // this thread's stores to the peer are ordered before whatever follows the block barrier
     __syncthreads();
     if (threadIdx.x == 0) {
       const int r = a.peer_rank[pi];
       if (atomicAdd(&a.arrived[r], 1u) == gridDim.x - 1) {
         a.arrived[r] = 0u;
-        __threadfence();
-        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.landed + r), "r"(a.epoch) : "memory");
+        __threadfence_system();
+        int* flag = reinterpret_cast<int*>(dst + a.sync_off) + kSyncLanded + a.rank;
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(a.epoch) : "memory");
       }
+    }
+  }
+}
+
+// One small block that returns once every other rank's shard of this epoch has landed (for launches that do not wait
+// themselves: ragged shards, the collective-free fallback order).
+__global__ void wait_shards_kernel(const int* landed, int world, int rank, int epoch) {
+  const int r = threadIdx.x;
+  if (r >= world || r == rank) return;
+  unsigned long long spins = 0;
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(landed + r) : "memory");
+    if (v - epoch >= 0) return;
+    __nanosleep(500);
+    if (++spins > 8000000ull) {  // ~4 s: a peer never pushed -- fail loudly instead of hanging the stream
+      printf("sclip: shard of rank %d never landed (epoch %d)\n", r, epoch);
+      __trap();
     }
   }
 }
@@ -954,30 +1025,37 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
 
 namespace sclip {
 
-int launch_pull_shards(const Workspace& w, const void* const* peer_ws, int first, int count, int max_blocks,
-                       int block_threads, int epoch, cudaStream_t stream) {
-  PullShardArgs a;
+int launch_push_shards(const Workspace& w, void* const* peer_ws, int max_blocks, int block_threads, int epoch,
+                       cudaStream_t stream) {
+  PushShardArgs a;
   memset(&a, 0, sizeof(a));
   const int world = w.pb.world, rank = w.pb.row_offset / w.pb.rows_local;
-  for (int i = 0; i < count; ++i) {
-    const int r = (rank + first + i) % world;
-    a.peer[i] = static_cast<const uint8_t*>(peer_ws[r]);
+  for (int i = 0; i + 1 < world; ++i) {
+    const int r = (rank + 1 + i) % world;
+    a.peer[i] = static_cast<uint8_t*>(peer_ws[r]);
     a.peer_rank[i] = r;
   }
-  a.count = count;
+  a.count = world - 1;
   a.local = w.base;
   a.xhat_off = w.lay.xhat;
   a.xhat_lo_off = w.lay.xhat_lo;
   a.diag_off = w.lay.diag_all;
+  a.sync_off = w.lay.sync;
   a.nseg = w.pb.math == SCLIP_MATH_F16X3 ? 6 : 3;
   a.rows_local = w.pb.rows_local;
   a.rows_global = w.pb.rows_global;
   a.dim = w.pb.dim;
-  a.landed = w.sync + kSyncLanded;
+  a.rank = rank;
   a.arrived = reinterpret_cast<unsigned int*>(w.sync) + kSyncArrived;
   a.epoch = epoch;
   const int bx = max_blocks < 1 ? 1 : max_blocks;
-  pull_shards_kernel<<<bx, block_threads, 0, stream>>>(a);
+  push_shards_kernel<<<bx, block_threads, 0, stream>>>(a);
+  SCLIP_LAUNCHED();
+  return SCLIP_OK;
+}
+
+int launch_wait_shards(const Workspace& w, int epoch, cudaStream_t stream) {
+  wait_shards_kernel<<<1, 32, 0, stream>>>(w.sync + kSyncLanded, w.pb.world, w.pb.row_offset / w.pb.rows_local, epoch);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
 }

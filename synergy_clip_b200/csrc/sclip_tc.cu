@@ -405,7 +405,8 @@ __device__ __forceinline__ Tile decode_similarity(int t, int nti_c, int ntj, int
 }
 
 // SCLIP_FWD_WAIT_PEERS: the tiles are taken wave by wave -- every (pair, row tile) on this rank's own columns first,
-// then on the columns of rank + 1, rank + 2, ... (the order in which sclip_pull_shards completes the shards).
+// then on the columns of rank - 1, rank - 2, ...: every rank pushes to rank + 1 first (sclip_push_shards), so the first
+// shard to land here is that of rank - 1, the second that of rank - 2, and so on.
 template <int CG>
 __device__ __forceinline__ Tile decode_forward(const FwdParams& P, int t, int npairs, int nti_c, int& wave) {
   if (!P.wait_peers) {
@@ -414,18 +415,19 @@ __device__ __forceinline__ Tile decode_forward(const FwdParams& P, int t, int np
   }
   const int per_wave = npairs * nti_c * P.tiles_per_rank;
   wave = t / per_wave;
-  return decode_similarity<CG>(t - wave * per_wave, nti_c, P.tiles_per_rank, P.tj_begin + wave * P.tiles_per_rank, P.ntj);
+  const int src = (P.world - wave) % P.world;  // ranks behind this one, modulo world
+  return decode_similarity<CG>(t - wave * per_wave, nti_c, P.tiles_per_rank, P.tj_begin + src * P.tiles_per_rank, P.ntj);
 }
 
-// Block until the shard of wave `wave` (source rank (rank + wave) % world) is complete in this workspace.
+// Block until the shard of wave `wave` (source rank (rank - wave) mod world) is complete in this workspace.
 __device__ __forceinline__ void wait_landed(const FwdParams& P, int wave) {
   if (wave <= 0) return;
-  const int* flag = P.landed + (P.rank + wave) % P.world;
+  const int* flag = P.landed + (P.rank + P.world - wave) % P.world;
   uint32_t spins = 0;
   uint64_t t0 = 0;
   for (;;) {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");  // written by the peer GPU
     if (v - P.epoch >= 0) return;
     __nanosleep(200);
     if ((++spins & 0xFFF) == 0) {

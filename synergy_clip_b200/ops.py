@@ -350,7 +350,7 @@ def _make_problem(img: torch.Tensor, cfg: TriContrastiveConfig) -> Tuple[Problem
     if math == "auto":
         math = "f16x3" if dtype == SCLIP_F32 else "f16"
     pb = Problem(rows_local=rows, rows_global=rows * world, row_offset=rows * rank, dim=dim, dtype=dtype,
-                 math=MATH_F16X3 if math == "f16x3" else MATH_F16, world=world, reserved=0)
+                 math=MATH_F16X3 if math == "f16x3" else MATH_F16, world=world, parity=0)
     return pb, world, rank
 
 
@@ -408,10 +408,12 @@ class _CudaBackend:
         _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), int(max_sms),
                                                       _stream()), "sclip_backward_gemms_role")
 
-    def pull_shards(self, ws, first, count, max_blocks, block_threads=1024, epoch=0):
-        _lib.check(self.lib.sclip_pull_shards(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(first), int(count),
-                                              int(max_blocks), int(block_threads), int(epoch), _stream()),
-                   "sclip_pull_shards")
+    def push_shards(self, ws, max_blocks, block_threads=1024, epoch=0):
+        _lib.check(self.lib.sclip_push_shards(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(max_blocks), int(block_threads),
+                                              int(epoch), _stream()), "sclip_push_shards")
+
+    def wait_shards(self, ws, epoch):
+        _lib.check(self.lib.sclip_wait_shards(byref(ws.pb), ws.ptr, int(epoch), _stream()), "sclip_wait_shards")
 
     def forward_loss_peers(self, ws, loss3):
         _lib.check(self.lib.sclip_forward_loss_peers(byref(ws.pb), ws.ptr, ws.peer_ptrs, _ptr(loss3), _stream()),
@@ -472,9 +474,11 @@ def _forward_stages(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig
     stash = bool(keep) and pb.math == MATH_F16 and (pb.dim >= 640 if cfg.stash == "auto" else bool(cfg.stash))
     ws.stashed = stash
     _mark("begin")
+    loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
+    if isinstance(ws, _SymmWorkspace):
+        return _forward_p2p(ws, img, txt, aud, t3, cfg, stash, loss3)
     be.prologue(ws, img, txt, aud, t3, diag=stash)
     _mark("prologue")
-    loss3 = torch.empty(3, dtype=torch.float32, device=img.device)
     if pb.world == 1:
         be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
         _mark("forward_tiles")
@@ -482,8 +486,6 @@ def _forward_stages(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig
         be.forward_loss(ws, None, loss3)
         _mark("forward_finish")
         return loss3
-    if isinstance(ws, _SymmWorkspace):
-        return _forward_p2p(ws, t3, cfg, stash, loss3)
     import torch.distributed as dist
 
     pg = cfg.process_group
@@ -535,51 +537,56 @@ def _forward_stages(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig
     return loss3
 
 
-def _forward_p2p(ws: "_SymmWorkspace", t3, cfg: TriContrastiveConfig, stash: bool, loss3: torch.Tensor):
-    """world > 1, workspace in symmetric memory.  After the prologue the operand shards of the other ranks are pulled
-    over NVLink by ONE `sclip_pull_shards` launch on the side stream (rank + 1 first, then rank + 2, ...), which
-    publishes a per-rank "landed" flag as each shard completes.  The similarity tiles are ONE persistent launch as well
-    (`SCLIP_FWD_WAIT_PEERS`): it takes this rank's own columns first and then the peers' in the same order, its TMA
-    producer acquiring the flag of a rank before the first tile on that rank's columns -- no host-side waves, no
-    per-wave launch / ramp / tail.  The pull kernel runs on the `comm_sms` SMs the tile kernel leaves free.
-    Barriers are the symmetric-memory signal pads (channel 0 on the side stream, 1 on the compute stream).
+def _forward_p2p(ws: "_SymmWorkspace", img, txt, aud, t3, cfg: TriContrastiveConfig, stash: bool, loss3: torch.Tensor):
+    """world > 1, workspace in symmetric memory (every rank's blob mapped into every process over NVLink / NVSwitch).
 
-    Cross-step ordering: a rank overwrites its shard (prologue) and its column statistics (forward_reduce) only after
-    every peer has finished reading the previous step's -- the peers' pulls complete before their tiles do, their
-    tiles before barrier 1, and barrier 0 of the next step follows every rank's `sclip_forward_loss_peers`."""
+    * all-gather of the operand shards = PUSH: after the prologue every rank writes its normalised shard straight into
+      the peers' workspaces (`sclip_push_shards`, side stream, rank + 1 first) and publishes a per-source "landed" flag
+      in each destination as it completes.  No barrier comes first: the exchange buffers exist twice and the steps
+      alternate between the copies (`problem.parity`), so a peer that is still finishing the previous step reads the
+      other copy.
+    * the similarity tiles are ONE persistent launch (`SCLIP_FWD_WAIT_PEERS`): this rank's own columns first, then the
+      peers' in arrival order (rank - 1, rank - 2, ...: everybody pushes to rank + 1 first), the TMA producer acquiring a rank's flag before the first tile on its columns -- no
+      host-side waves, no per-wave launch / ramp / tail.  The push kernel runs on the `comm_sms` SMs the tiles leave.
+    * statistics: one signal-pad barrier behind `sclip_forward_reduce`, then `sclip_forward_loss_peers` reads every
+      rank's column statistics and row terms from the peers and computes the complete losses.
+
+    Why a shard may be overwritten: rank r pushes step n + 1 into copy (n + 1) % 2 of peer q.  That copy was last read
+    by q in step n - 1; q's push of step n -- which r has consumed, or it could not be in step n + 1 -- was enqueued
+    behind q's whole step n - 1.  The column statistics a peer reads are rewritten one `sclip_forward_reduce` later,
+    which lies behind the next step's tiles, which wait for every rank's next push, which lies behind that rank's
+    `sclip_forward_loss_peers` of this step."""
     be = _BACKEND
     pb, lay, hdl = ws.pb, ws.lay, ws.hdl
-    bl, world = pb.rows_local, pb.world
+    bl = pb.rows_local
     dev = ws.blob.device
     cur = torch.cuda.current_stream()
     comm = _comm_stream(dev)
-    # the in-kernel wait needs the pull kernel to be resident next to the tile kernel: it gets its own SMs
-    pipelined = cfg.overlap and bl % 256 == 0 and cfg.comm_sms > 0
-    # pull kernel: 1024-thread blocks, two per SM left free by the tile kernel.  Measured at 8 GPUs (B = 32768, D = 768):
-    # 20 reserved SMs beat 12, and 256-thread blocks co-resident with the tile CTAs (no reserved SMs) were slower still.
-    blocks = 2 * max(cfg.comm_sms, 4)
     ws.epoch += 1
+    pb.parity = ws.epoch & 1
+    be.prologue(ws, img, txt, aud, t3, diag=stash)
+    _mark("prologue")
+    # the in-kernel wait needs the push kernels of all ranks to make progress next to the tile kernels: own SMs
+    pipelined = cfg.overlap and bl % 256 == 0 and cfg.comm_sms > 0
+    blocks = 2 * max(cfg.comm_sms, 4)  # 1024-thread blocks, two per SM left free by the tile kernel
     ready = torch.cuda.Event()
     ready.record(cur)
     trace = _TRACE is not None
-    pulled = torch.cuda.Event(enable_timing=trace)
-    after_barrier = torch.cuda.Event(enable_timing=True) if trace else None
+    pushed = torch.cuda.Event(enable_timing=trace)
     with torch.cuda.stream(comm):
         comm.wait_event(ready)
-        hdl.barrier(0)  # every rank's own shard is normalised and in place
-        if trace:
-            after_barrier.record(comm)
-        be.pull_shards(ws, 1, world - 1, blocks, 1024, ws.epoch)
-        pulled.record(comm)
+        be.push_shards(ws, blocks, 1024, ws.epoch)
+        pushed.record(comm)
     if trace:
         global _LAST_COMM_EVENTS
-        _LAST_COMM_EVENTS = [("fwd_barrier", after_barrier), ("pulls", pulled)]
+        _LAST_COMM_EVENTS = [("pushes", pushed)]
     if pipelined:
         be.forward_tiles_cols(ws, t3, 7, 0, 0, stash, max_sms=_sm_count(dev) - cfg.comm_sms, wait_epoch=ws.epoch)
-        cur.wait_event(pulled)  # (already implied by the kernel's own waits; keeps the stream order explicit)
     else:
-        cur.wait_event(pulled)
+        # ragged shards, or no SMs set aside for the pushes: wait for every shard first, then the plain column order
+        be.wait_shards(ws, ws.epoch)
         be.forward_tiles_cols(ws, t3, 7, 0, lay.col_tiles, stash)
+    cur.wait_event(pushed)  # this rank's own pushes are out before anything may rewrite the shard
     _mark("forward_tiles")
     be.forward_reduce(ws)
     _mark("forward_reduce")

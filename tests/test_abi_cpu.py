@@ -44,7 +44,7 @@ def test_plan_layout_is_consistent():
     dict(rows_local=128, rows_global=64), dict(row_offset=200),
 ])
 def test_plan_rejects_bad_problems(bad):
-    kw = dict(rows_local=128, rows_global=128, row_offset=0, dim=512, dtype=0, math=0, world=1, reserved=0)
+    kw = dict(rows_local=128, rows_global=128, row_offset=0, dim=512, dtype=0, math=0, world=1, parity=0)
     kw.update(bad)
     lay = _lib.Layout()
     rc = _lib.load().sclip_plan(ctypes.byref(_lib.Problem(**kw)), ctypes.byref(lay))
@@ -83,12 +83,15 @@ def test_peer_memory_and_scorer_calls_validate_their_arguments():
     fake_ws = ctypes.c_void_p(1 << 20)                                                         # 256-byte aligned, never touched
     single = _lib.Problem(128, 128, 0, 512, 1, 0, 1, 0)
     table = (ctypes.c_void_p * 2)(1 << 20, 2 << 20)
-    assert lib.sclip_pull_shards(ctypes.byref(single), fake_ws, table, 1, 1, 8, 256, 1, None) == -1  # world must be >= 2
+    assert lib.sclip_push_shards(ctypes.byref(single), fake_ws, table, 8, 256, 1, None) == -1        # world must be >= 2
     sharded = _lib.Problem(128, 256, 128, 512, 1, 0, 2, 0)                                     # rank 1 of 2
-    assert lib.sclip_pull_shards(ctypes.byref(sharded), fake_ws, table, 1, 1, 8, 256, 1, None) == -1  # peer_ws[rank] != ws
+    assert lib.sclip_push_shards(ctypes.byref(sharded), fake_ws, table, 8, 256, 1, None) == -1       # peer_ws[rank] != ws
     assert b"own workspace" in lib.sclip_last_error()
     assert lib.sclip_pull_reduce_cols(ctypes.byref(sharded), fake_ws, None, 8, 256, None) == -1
     assert lib.sclip_forward_loss_peers(ctypes.byref(sharded), fake_ws, None, None, None) == -1
+    assert lib.sclip_wait_shards(ctypes.byref(single), fake_ws, 1, None) == -1
+    bad_parity = _lib.Problem(128, 128, 0, 512, 1, 0, 1, 1)                                    # parity needs world > 1
+    assert lib.sclip_plan(ctypes.byref(bad_parity), ctypes.byref(_lib.Layout())) == -1
     # the single-launch forward (SCLIP_FWD_WAIT_PEERS = 4) needs equal shards that are multiples of 256 rows
     t3 = ctypes.c_void_p(4 << 20)
     assert lib.sclip_forward_tiles_cols(ctypes.byref(sharded), fake_ws, t3, 7, 0, 0, 4, 128, 1, None) == -1

@@ -34,7 +34,7 @@ def test_two_call_abi_matches_oracle(b, d, dtype_name, math, tol):
     want = closed_form.tri_contrastive(*embs, t3v, g3v)
     img, txt, aud = [torch.from_numpy(e).cuda().to(dtype) for e in embs]
     pb = _lib.Problem(rows_local=b, rows_global=b, row_offset=0, dim=d, dtype=0 if dtype == torch.float32 else 1,
-                      math=math, world=1, reserved=0)
+                      math=math, world=1, parity=0)
     lay = _lib.Layout()
     assert lib.sclip_plan(byref(pb), byref(lay)) == 0
     ws = torch.empty(int(lay.total_bytes) + 256, dtype=torch.uint8, device="cuda")

@@ -2,7 +2,7 @@
 
 Every "rank" is a workspace of its own on the same device and `peer_ws` is the table of those workspaces -- exactly
 what the symmetric-memory mapping gives a real multi-GPU run, except that the peers' bytes come through local loads
-instead of NVLink loads.  That exercises `sclip_pull_shards` (including the per-rank "landed" flags), the single-launch
+instead of NVLink loads.  That exercises `sclip_push_shards` (including the per-rank "landed" flags and the two-copy exchange buffers), the single-launch
 forward that waits on those flags (`SCLIP_FWD_WAIT_PEERS`), `sclip_forward_loss_peers`, the role-split gradient GEMMs
 and `sclip_pull_reduce_cols` with the same kernels, launch arguments and workspace layout as `ops._forward_p2p` /
 `ops._backward_impl`; the result is compared with the oracle on the concatenated batch (SURVEY 8e parity definition).
@@ -66,11 +66,14 @@ def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch,
     for step in range(1, steps + 1):  # two steps on the same workspaces: the epoch flags must not be stale
         loss = [torch.empty(3, device="cuda") for _ in range(world)]
         for r, rk in enumerate(ranks):
+            rk.pb.parity = step & 1  # the two copies of the exchange buffers alternate
             _lib.check(lib.sclip_prologue(byref(rk.pb), rk.ptr, *[_p(x) for x in shards[r]], _p(t3), 1 if stash else 0, st),
                        "prologue")
-        for rk in ranks:  # (a real run: barrier, then this on the side stream)
-            _lib.check(lib.sclip_pull_shards(byref(rk.pb), rk.ptr, table, 1, world - 1, 8, 1024, step, st), "pull_shards")
+        for rk in ranks:  # (a real run: on the side stream, concurrently with the tiles)
+            _lib.check(lib.sclip_push_shards(byref(rk.pb), rk.ptr, table, 8, 1024, step, st), "push_shards")
         for rk in ranks:
+            if not single_launch:
+                _lib.check(lib.sclip_wait_shards(byref(rk.pb), rk.ptr, step, st), "wait_shards")
             flags = (1 if stash else 0) | (4 if single_launch else 0)
             _lib.check(lib.sclip_forward_tiles_cols(byref(rk.pb), rk.ptr, _p(t3), 7, 0, 0 if single_launch else col_tiles,
                                                     flags, 100, step, st), "forward_tiles_cols")

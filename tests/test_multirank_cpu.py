@@ -190,7 +190,7 @@ def _wave_major_order(world, rank, tiles_per_rank, npairs, row_tiles):
         first = group * 8
         gm = min(row_tiles - first, 8)
         ti, tj = first + r % gm, r // gm
-        tj = (rank * tiles_per_rank + wave * tiles_per_rank + tj) % col_tiles
+        tj = (rank * tiles_per_rank + ((world - wave) % world) * tiles_per_rank + tj) % col_tiles
         out.append((wave, pair, ti, tj))
     return out
 
@@ -198,8 +198,9 @@ def _wave_major_order(world, rank, tiles_per_rank, npairs, row_tiles):
 @pytest.mark.parametrize("world,row_tiles", [(2, 8), (3, 5), (4, 16), (8, 8), (16, 3)])
 def test_wave_major_tile_order_matches_the_pull_order(world, row_tiles):
     """Host-side model of the single-launch peer-memory forward: every (pair, row tile, column tile) is taken exactly
-    once, wave w only touches the columns of rank + w -- the shard `sclip_pull_shards` completes w-th -- and wave 0 is
-    this rank's own columns, so the kernel never needs a shard earlier than the pull kernel delivers it."""
+    once, wave 0 is this rank's own columns and wave w only touches the columns of rank - w.  Every rank pushes its
+    shard to rank + 1 first, rank + 2 second, ... (`sclip_push_shards`), so the shard of rank - w is the w-th to land
+    here: the kernel never needs a shard earlier than the exchange delivers it."""
     tiles_per_rank, npairs = 3, 3
     for rank in range(world):
         order = _wave_major_order(world, rank, tiles_per_rank, npairs, row_tiles)
@@ -207,4 +208,4 @@ def test_wave_major_tile_order_matches_the_pull_order(world, row_tiles):
         waves = [w for w, _, _, _ in order]
         assert waves == sorted(waves)
         for wave, _, _, tj in order:
-            assert tj // tiles_per_rank == (rank + wave) % world
+            assert tj // tiles_per_rank == (rank - wave) % world

@@ -6,6 +6,8 @@ tensor-core peak).
     python bench.py --workload cfg1|cfg2|north_star          # BASELINE.json configs 1-3 as the headline of the line
     python bench.py --workload sweep [--gpus N]              # BASELINE config 5: B x D sweep, one JSON line per point
                                                              # into gpurun_out/sweep_w<N>.jsonl (+ one summary line)
+    python bench.py --workload step [--gpus N]               # BASELINE config 4: full Base pre-training step (encoders +
+                                                             # loss tail, DDP, AdamW) on synthetic inputs, six arms
     python bench.py --impl reference [--workload ...]        # the reference's PyTorch CPU loss path (oracle port)
 
 One "step" = one forward + backward of the loss tail (model.py:247-272 + autograd) over one synthetic global
@@ -326,7 +328,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS) + ["sweep"])
+    ap.add_argument("--workload", default="north_star", choices=sorted(WORKLOADS) + ["sweep", "step"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip configs 1 / 2 and the GPU-eager baseline")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: run the collectives on the compute stream")
@@ -441,6 +443,8 @@ def main():
 
     if args.workload == "sweep":
         return run_sweep(args, measure, world, rank, peaks, dist)
+    if args.workload == "step":
+        return run_step(args, world, rank, dev, dist)
 
     b, d, dt_name = WORKLOADS[args.workload]
     shard = args.workload == "north_star"
@@ -593,6 +597,153 @@ def run_sweep(args, measure, world, rank, peaks, dist):
             "config": {"workload": "BASELINE config 5: global-batch sweep 4k-128k x dim 512/768/1024 (value = the best point)",
                        "points_file": os.path.relpath(path, ROOT)},
             "sweep": points}), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_step(args, world, rank, dev, dist):
+    """BASELINE config 4 / SURVEY 8(f3): the loop body of main_pretraining.py:158-177 (DDP wrap :138, AdamW :139, three
+    weighted losses, four `.item()` reads per micro-batch, `loss / accumulation_steps`, `.backward()`, optimizer step
+    every 4 micro-batches) on the Base configuration (config.py: ViT-B/16, RoBERTa-base-sized text model, AST-base,
+    projection 768) with HF-config-initialised random weights (no network: no checkpoints) and synthetic 224^2 images /
+    32-token text / 1024 x 128 spectrograms, per-GPU micro-batch 35 (main_pretraining.py:79).  Arms: the reference's own
+    tail statements, the fused tail on the local batch, the fused tail on the global batch (negatives from all ranks);
+    each in the reference's regime (fp32, gradient all-reduce on every micro-step) and with bf16 autocast + `no_sync`
+    on the non-boundary micro-steps.  Reports ms per optimizer step and the share of the loss tail."""
+    import contextlib
+    import types
+
+    import torch
+    import transformers
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from transformers import (ASTConfig, ASTModel, CLIPVisionConfig, CLIPVisionModel, RobertaConfig, RobertaModel)
+
+    from synergy_clip_b200.model import Tri_CLIP
+
+    transformers.CLIPVisionModel.from_pretrained = staticmethod(lambda path: CLIPVisionModel(CLIPVisionConfig(
+        hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, image_size=224,
+        patch_size=16)))
+    transformers.AutoModel.from_pretrained = staticmethod(lambda path: RobertaModel(RobertaConfig(
+        hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, vocab_size=50265,
+        max_position_embeddings=514)))
+    transformers.ASTModel.from_pretrained = staticmethod(lambda path: ASTModel(ASTConfig(
+        hidden_size=768, intermediate_size=3072, num_hidden_layers=12, num_attention_heads=12, max_length=1024,
+        num_mel_bins=128, patch_size=16)))
+
+    class _Sub:
+        output_attentions = False
+        output_hidden_states = False
+        hidden_size = 768
+
+    cfg = types.SimpleNamespace(vision_config=_Sub, text_config=_Sub, audio_config=_Sub, projection_dim=768,
+                                logit_scale_init_value=LOGIT_SCALE_INIT, return_dict=False, is_PT=True,
+                                return_logits=False, return_lhs=False)
+    micro, accum = 35, 4  # main_pretraining.py:79-80 (Base)
+    steps, warmup = min(args.steps, 3), 1
+    torch.manual_seed(17)
+    model = Tri_CLIP(cfg).to(dev)
+    ddp = DDP(model, device_ids=[dev.index]) if world > 1 else model
+    opt = torch.optim.AdamW(ddp.parameters(), lr=5e-6)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    batch = dict(pixel_values=torch.randn(micro, 3, 224, 224, device=dev, generator=g),
+                 input_ids=torch.randint(3, 50000, (micro, 32), device=dev, generator=g),
+                 att_mask=torch.ones(micro, 32, dtype=torch.long, device=dev),
+                 input_values=torch.randn(micro, 1024, 128, device=dev, generator=g))
+
+    def optimizer_step(autocast, use_no_sync):
+        logged = 0.0
+        opt.zero_grad()
+        for i in range(accum):
+            sync_ctx = ddp.no_sync() if (use_no_sync and world > 1 and i + 1 < accum) else contextlib.nullcontext()
+            amp = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+            with sync_ctx:
+                with amp:
+                    out = ddp(**batch)
+                it, ta, ai = out[0] * 1.0, out[1] * 1.0, out[2] * 1.0
+                loss = it + ta + ai
+                logged += loss.item() + it.item() + ta.item() + ai.item()  # the four reads of :169-170
+                (loss / accum).backward()
+        opt.step()
+        return logged
+
+    def time_arm(env, autocast, use_no_sync):
+        for k in ("SCLIP_REFERENCE_TAIL", "SCLIP_GLOBAL_BATCH", "SCLIP_FUSED_PROJECTION"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        for _ in range(warmup):
+            optimizer_step(autocast, use_no_sync)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            optimizer_step(autocast, use_no_sync)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    arms = {}
+    for regime, (autocast, ns) in (("fp32_allreduce_every_microstep", (False, False)), ("bf16_autocast_no_sync", (True, True))):
+        arms[regime] = {
+            "reference_tail": time_arm({"SCLIP_REFERENCE_TAIL": "1"}, autocast, ns),
+            "fused_tail_local_batch": time_arm({}, autocast, ns),
+            "fused_tail_global_batch": time_arm({"SCLIP_GLOBAL_BATCH": "1"}, autocast, ns) if world > 1 else None,
+            "fused_projection_and_tail": time_arm({"SCLIP_FUSED_PROJECTION": "1"}, autocast, ns),
+        }
+    # the loss tail alone at the shapes this step feeds it (local 35 x 768; global 35 * world x 768), fwd + bwd
+    from synergy_clip_b200 import ops
+
+    def tail_ms(rows, fused):
+        e = [torch.randn(rows, 768, device=dev, generator=g).requires_grad_(True) for _ in range(3)]
+        t = [torch.tensor(LOGIT_SCALE_INIT, device=dev, requires_grad=True) for _ in range(3)]
+
+        def run():
+            if fused:
+                for p in (*e, *t):
+                    p.grad = None
+                a, b, c = ops.fused_tri_contrastive(*e, *t)
+                (a + b + c).backward()
+            else:
+                reference_tail_eager(*e, t)
+
+        for _ in range(5):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(30):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 30
+
+    tails = {"reference_eager_local_ms": tail_ms(micro, False), "fused_local_ms": tail_ms(micro, True),
+             "reference_eager_global_rows_ms": tail_ms(micro * world, False),
+             "fused_global_rows_ms_single_gpu": tail_ms(micro * world, True)}
+    if rank == 0:
+        base = arms["fp32_allreduce_every_microstep"]["reference_tail"]
+        best = arms["bf16_autocast_no_sync"]["fused_tail_local_batch"]
+        print(json.dumps({
+            "metric": "pretraining_step_samples_per_sec", "value": micro * accum * world / (best * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": best, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4: Synergy-CLIP Base pre-training step (ViT-B/16 + RoBERTa-base-sized "
+                                   "text + AST-base encoders, random init, fused loss tail), synthetic 224^2 images / 32 "
+                                   "tokens / 1024x128 spectrograms, micro-batch 35 per GPU x 4 accumulation steps, DDP + "
+                                   "AdamW; value = the bf16-autocast + no_sync arm with the fused tail",
+                       "micro_batch_per_gpu": micro, "accumulation_steps": accum},
+            "ms_per_optimizer_step": arms,
+            "speedup_vs_reference_regime": base / best,
+            "loss_tail_alone_ms": tails,
+            "loss_tail_share_of_microstep": {
+                "reference_fp32": tails["reference_eager_local_ms"] / (base / accum),
+                "fused_bf16": tails["fused_local_ms"] / (best / accum)},
+        }), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -137,11 +137,26 @@ class Tri_CLIP(nn.Module):
         vision_out = self._vision(pixel_values)
         text_out = self._text(input_ids, att_mask, pos_ids)
         audio_out = self._audio(input_values, head_mask)
+        if (self.config.is_PT and os.environ.get("SCLIP_FUSED_PROJECTION", "0") == "1" and vision_out[1].is_cuda
+                and os.environ.get("SCLIP_REFERENCE_TAIL", "0") != "1"):
+            # model.py:234-272 as one node: the three projection GEMMs, the tail and the heads' backward GEMMs on the
+            # library's tile kernels (fp16 tensor-core operands, see projection.py)
+            from .projection import projected_tri_contrastive
+
+            return projected_tri_contrastive(vision_out[1], text_out[1], audio_out[1], self.vision_projection.weight,
+                                             self.text_projection.weight, self.audio_projection.weight,
+                                             self.logit_scale_for_IT, self.logit_scale_for_TA, self.logit_scale_for_AI,
+                                             config=_op_config())
         img = self.vision_projection(vision_out[1])
         txt = self.text_projection(text_out[1])
         aud = self.audio_projection(audio_out[1])
 
         if self.config.is_PT:
+            if os.environ.get("SCLIP_REFERENCE_TAIL", "0") == "1":
+                # A/B switch for measurements (bench.py --workload step): the reference's own statements, model.py:247-272
+                return (clip_loss(_scaled_cosine(img, txt, self.logit_scale_for_IT)),
+                        clip_loss(_scaled_cosine(txt, aud, self.logit_scale_for_TA)),
+                        clip_loss(_scaled_cosine(aud, img, self.logit_scale_for_AI)))
             # model.py:247-272 as one fused op: (IT_loss, TA_loss, AI_loss), each a differentiable 0-dim tensor
             return fused_tri_contrastive(img, txt, aud, self.logit_scale_for_IT, self.logit_scale_for_TA,
                                          self.logit_scale_for_AI, config=_op_config())

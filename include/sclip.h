@@ -94,8 +94,9 @@ typedef struct sclip_layout {
   uint64_t col_contrib;   /* [3][rows_local][dim] fp32 landing buffer of that reduce-scatter (world > 1 only)            */
   uint64_t diag_all;      /* [3][rows_global] fp32 positive-pair logits of ALL rows (stash scaling); sclip_forward_diag
                              writes this rank's rows [exchange: all-gather when world > 1]                     */
-  uint64_t fac_row;       /* [3][2][rows_local rounded up to 64] fp32 row factors of the stash -> G' conversion */
-  uint64_t fac_col;       /* [3][2][rows_global rounded up to 64] fp32 column factors                           */
+  uint64_t fac_row;       /* [3][2][rows_local rounded up to 64] fp32 row factors of the stash -> G' conversion,
+                             followed by the same values pair-interleaved [3][ld/2][4] (converting GEMM)         */
+  uint64_t fac_col;       /* [3][2][rows_global rounded up to 64] fp32 column factors, likewise                  */
   uint64_t dot_part;      /* [3][ceil(rows_local/8)] fp32 partial sums of <xhat, dxhat> (stash mode dlogit_scale) */
   uint64_t status;        /* [4] int32 device-side status words (bit 0: a row/column sum under- or overflowed);
                              cleared by sclip_prologue, read back by sclip_read_status                            */
@@ -201,9 +202,19 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
 #define SCLIP_ROLE_BOTH 0
 #define SCLIP_ROLE_COLUMN 1
 #define SCLIP_ROLE_ROW 2
-/* max_sms > 0: at most that many SMs (see sclip_forward_tiles_cols). */
+/* flags & SCLIP_GEMM_CONVERT_STASH: grad_tiles still holds the forward's stash E~ (no sclip_backward_scale ran):
+ * G' = E~ (R1 C1 + R2 C2) - kappa c_p I is formed inside the A-operand path of the GEMM kernel (converted tiles go
+ * through tensor memory, never back to HBM or shared memory) from the factor arrays of sclip_backward_factors.  The
+ * values are those of sclip_backward_scale + the plain GEMMs, bit for bit.  Only where sclip_gemm_converts_stash()
+ * says so (fp16 operands and gradient tiles of 384 columns, e.g. dim 768).  The stash survives the call.
+ * max_sms > 0: at most that many SMs (see sclip_forward_tiles_cols). */
+#define SCLIP_GEMM_CONVERT_STASH 1
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
-                              int max_sms, void* stream);
+                              int flags, int max_sms, void* stream);
+int sclip_gemm_converts_stash(const sclip_problem* problem); /* 1 | 0; pure host arithmetic */
+/* The per-row / per-column factors of the stash -> G' conversion (fac_row, fac_col) alone: what a converting GEMM
+ * needs instead of sclip_backward_scale. */
+int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
 /* Backward of the normalisation: d x = (d - xhat <xhat, d>) / ||x|| with d = dxhat_row (+ col_contrib, the
  * reduce-scattered column-role gradients [3][rows_local][dim] fp32, NULL when world == 1), times grad_mult

@@ -42,6 +42,7 @@ struct Segment {
   int a_mn;    // 0: operand stored [rows][k] (K-major)   1: stored [k][rows] (MN-major)
   int b_mn;
   int num_kb;  // number of BK-wide k blocks
+  int pair;    // converting GEMM: the pair whose stash this segment reads (factor lookup); else unused
 };
 
 struct Job {
@@ -180,6 +181,11 @@ struct GemmParams {
   const float* g3;
   const float* log_alpha;  // when non-null alpha is further multiplied by exp(*log_alpha) (zero-shot scorers)
   float alpha0;
+  // converting GEMM (gemm_conv_kernel): the A operand is the forward's stash E~; G' = E~ (R1 C1 + R2 C2) - kappa c_p I is
+  // formed on the fly from the factor arrays of sclip_backward_factors
+  const float* fac_row;  // [3][2][ld_row]
+  const float* fac_col;  // [3][2][ld_col]
+  int ld_row, ld_col, row_offset;
 };
 
 // cg = 1: one CTA per tile of 128 rows; cg = 2: CTA pairs (cta_group::2) on tiles of 256 rows
@@ -190,6 +196,10 @@ int launch_backward_tiles(const BwdParams& p, int cg, int ew, cudaStream_t strea
 int launch_gemm(const GemmParams& p, int cg, int ew, int max_sms, cudaStream_t stream);
 // CTA pairs on 256 x wn tiles with one accumulator (MN-major B operands only); see gemm_wide_kernel
 int launch_gemm_wide(const GemmParams& p, int ew, int max_sms, cudaStream_t stream);
+// the same tiles (wn = 384 only) with the stash -> G' conversion in the A-operand path (TMEM)
+int launch_gemm_conv(const GemmParams& p, int max_sms, cudaStream_t stream);
+int conv_stages();
+int launch_backward_factors(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream);
 int wide_stages(int wn);  // depth of the TMA ring that fits beside nothing else in shared memory
 int cta_group();   // SCLIP_CTA_GROUP environment override (1 or 2), default 2
 int epi_warps();   // SCLIP_EPI_WARPS environment override (8 or 16), default 16

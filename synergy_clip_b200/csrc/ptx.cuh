@@ -304,6 +304,54 @@ __device__ __forceinline__ void umma_commit_2sm_u32(uint32_t bar, uint16_t cta_m
                "h"(cta_mask)
                : "memory");
 }
+// ---- TMEM as the A operand (tcgen05.mma "TS" form) -- used by the gradient GEMM that converts its stash tiles on the fly
+// D[tmem] (+)= A[tmem] * B[smem desc].  A in TMEM: lane = row of this CTA's half of M, one 32-bit column = two
+// consecutive k elements (fp16), i.e. 8 columns per K = 16 instruction.
+__device__ __forceinline__ void umma_f16_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: thread t of the warp writes lane (base + t), 16 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// registers -> TMEM, mma-fragment layout: 16 lanes x 256 bit, 2 repetitions along the columns (16 columns):
+//   v[4 n + 2 h + c] -> lane (base + 8 h + t / 4), column (8 n + 2 (t % 4) + c)
+__device__ __forceinline__ void tmem_st_16x256b_x2(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// four transposed 8 x 8 b16 matrices from shared memory: lane L supplies the address of row (L & 7) of matrix (L >> 3);
+// thread t receives, of matrix j, the elements (row 2 (t % 4), col t / 4) and (row 2 (t % 4) + 1, col t / 4) in r[j]
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t smem_addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_addr));
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_u32(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(bar)
+      : "memory");
+}
 // Shared-memory matrix descriptor split into its two words: the high word (stride byte offset, version, swizzle) is a
 // constant of the operand layout, the low word is (address >> 4) | (leading byte offset >> 4) << 16, so stepping through
 // a stage or along k is one 32-bit add.

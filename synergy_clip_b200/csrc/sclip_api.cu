@@ -180,8 +180,8 @@ int plan(const sclip_problem* pb, sclip_layout* lay) {
   lay->dxhat_col = pb->world > 1 ? take(3 * bg * d * 4) : lay->dxhat_row;
   lay->col_contrib = pb->world > 1 ? take(3 * bl * d * 4) : lay->dxhat_row;
   lay->diag_all = take(copies * 3 * bg * 4) + par * 3 * bg * 4;
-  lay->fac_row = take(3 * 2 * align_up(bl, 64) * 4);
-  lay->fac_col = take(3 * 2 * align_up(bg, 64) * 4);
+  lay->fac_row = take(2 * 3 * 2 * align_up(bl, 64) * 4);  // planar [3][2][ld] + pair-interleaved [3][ld/2][4]
+  lay->fac_col = take(2 * 3 * 2 * align_up(bg, 64) * 4);
   lay->dot_part = take(3 * ((bl + 7) / 8) * 4);
   lay->status = take(4 * 4);
   lay->rowterm_part = take(3 * static_cast<uint64_t>(reduce_row_blocks(*pb) + loss_col_chunks(*pb)) * 8);
@@ -591,11 +591,27 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
 }
 
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
-  return sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, stream);
+  return sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, 0, stream);
+}
+
+int sclip_gemm_converts_stash(const sclip_problem* problem) {
+  if (check_problem(problem)) return 0;
+  return (problem->math == SCLIP_MATH_F16 && wide_enabled() && wide_width(problem->dim) == 384) ? 1 : 0;
+}
+
+int sclip_backward_factors(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
+  Workspace w;
+  int rc = resolve(problem, ws, &w);
+  if (rc) return rc;
+  if (t3 == nullptr || g3 == nullptr || w.pb.math != SCLIP_MATH_F16) {
+    set_error("sclip_backward_factors needs t3, g3 and a SCLIP_MATH_F16 problem");
+    return SCLIP_ERR_ARGUMENT;
+  }
+  return launch_backward_factors(w, t3, g3, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,
-                              int max_sms, void* stream) {
+                              int flags, int max_sms, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
   if (rc) return rc;
@@ -629,6 +645,12 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
   }
   int nj = 0, tiles = 0;
   if (max_sms < 0) max_sms = 0;
+  const bool convert = (flags & SCLIP_GEMM_CONVERT_STASH) != 0;
+  if (convert && !sclip_gemm_converts_stash(problem)) {
+    set_error("SCLIP_GEMM_CONVERT_STASH needs SCLIP_MATH_F16 and a dim whose gradient tiles are 384 columns wide "
+              "(sclip_gemm_converts_stash)");
+    return SCLIP_ERR_ARGUMENT;
+  }
   auto add_role = [&](Job& job, int m, bool row_role) {
     if (row_role) {  // G'_{pair m} (rows_local x rows_global, K-major) . xhat_{col modality} (k = global row)
       const int pr = modality_row_pair(m), cm = pair_col_modality(pr);
@@ -636,14 +658,16 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
         job.seg[job.nseg++] = seg(tab.use(kGloK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
         job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXloAllMN + cm), 0, 1, kb_g);
       }
-      job.seg[job.nseg++] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
+      job.seg[job.nseg] = seg(tab.use(kGK + pr), tab.use(kXhatAllMN + cm), 0, 1, kb_g);
+      job.seg[job.nseg++].pair = pr;
     } else {  // G'^T_{pair (m+2)%3} (rows_global x rows_local, MN-major view of G') . xhat_{row modality} (k = local row)
       const int pc = modality_col_pair(m), rm = pair_row_modality(pc);
       if (x3) {
         job.seg[job.nseg++] = seg(tab.use(kGloMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
         job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXloLocMN + rm), 1, 1, kb_l);
       }
-      job.seg[job.nseg++] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
+      job.seg[job.nseg] = seg(tab.use(kGMN + pc), tab.use(kXhatLocMN + rm), 1, 1, kb_l);
+      job.seg[job.nseg++].pair = pc;
     }
   };
   for (int m = 0; m < 3 && do_row; ++m) {
@@ -704,6 +728,15 @@ int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const floa
       if (do_col) SCLIP_CUDA_OK(cudaMemsetAsync(w.dxhat_col, 0, 3 * bg * d * 4, st));
     }
     p.total_tiles = tiles;
+    if (convert) {  // the A operand is the forward's stash: G' is formed in the A-operand path (gemm_conv_kernel)
+      p.fac_row = w.fac_row;
+      p.fac_col = w.fac_col;
+      p.ld_row = static_cast<int>(align_up(pb.rows_local, 64));
+      p.ld_col = static_cast<int>(align_up(pb.rows_global, 64));
+      p.row_offset = pb.row_offset;
+      p.stages = conv_stages();
+      return launch_gemm_conv(p, max_sms, st);
+    }
     p.stages = wide_stages(p.wn);
     return launch_gemm_wide(p, epi_warps(), max_sms, st);
   }
@@ -966,7 +999,7 @@ int sclip_backward(const sclip_problem* problem, void* ws, const void* img, cons
   const bool stashed = kept == 2;
   set_kept(ws, 0);
   int rc = stashed ? sclip_backward_scale(problem, ws, t3, g3, stream) : sclip_backward_tiles(problem, ws, t3, g3, stream);
-  if (!rc) rc = sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, stream);
+  if (!rc) rc = sclip_backward_gemms_role(problem, ws, t3, g3, SCLIP_ROLE_BOTH, 0, 0, stream);
   if (!rc)
     rc = sclip_backward_finish(problem, ws, img, txt, aud, t3, g3, nullptr, 1.0f, dimg, dtxt, daud, out_f32,
                                stashed ? SCLIP_BWD_STASHED : 0, dt3, stream);

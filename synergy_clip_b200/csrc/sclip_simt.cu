@@ -610,6 +610,11 @@ __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs 
     }
     a.fac_row[(static_cast<size_t>(p) * 2 + 0) * a.ld_row + i] = r1;
     a.fac_row[(static_cast<size_t>(p) * 2 + 1) * a.ld_row + i] = r2;
+    // the same factors interleaved by pairs of rows -- (R1_i, R1_i+1, R2_i, R2_i+1) -- behind the planar arrays: what
+    // the converting GEMM bulk-loads per k block and reads as packed fp32 pairs
+    float* pk = a.fac_row + static_cast<size_t>(3) * 2 * a.ld_row + (static_cast<size_t>(p) * (a.ld_row / 2) + i / 2) * 4;
+    pk[i & 1] = r1;
+    pk[2 + (i & 1)] = r2;
   }
   if (i < a.ld_col) {
     float c1 = 0.f, c2 = 0.f;
@@ -620,6 +625,9 @@ __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs 
     }
     a.fac_col[(static_cast<size_t>(p) * 2 + 0) * a.ld_col + i] = c1;
     a.fac_col[(static_cast<size_t>(p) * 2 + 1) * a.ld_col + i] = c2;
+    float* pk = a.fac_col + static_cast<size_t>(3) * 2 * a.ld_col + (static_cast<size_t>(p) * (a.ld_col / 2) + i / 2) * 4;
+    pk[i & 1] = c1;
+    pk[2 + (i & 1)] = c2;
   }
 }
 
@@ -1006,13 +1014,20 @@ int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream) {
   return SCLIP_OK;
 }
 
-int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
+int launch_backward_factors(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
   const int ld_row = (w.pb.rows_local + 63) / 64 * 64, ld_col = (w.pb.rows_global + 63) / 64 * 64;
   FactorArgs f{t3, g3, w.diag_all, w.lse_row, w.lse_col, w.fac_row, w.fac_col,
                w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, ld_row, ld_col};
   const int n = ld_row > ld_col ? ld_row : ld_col;
   backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
   SCLIP_LAUNCHED();
+  return SCLIP_OK;
+}
+
+int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
+  const int rc = launch_backward_factors(w, t3, g3, stream);
+  if (rc) return rc;
+  const int ld_row = (w.pb.rows_local + 63) / 64 * 64, ld_col = (w.pb.rows_global + 63) / 64 * 64;
   ScaleArgs a{w.g[0], w.fac_row, w.fac_col, t3, g3, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col,
               w.pb.row_offset};
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);

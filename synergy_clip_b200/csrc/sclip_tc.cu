@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -1544,6 +1545,460 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) gemm_wide_kernel(const __grid
   }
 }
 
+// ============================================================================================== converting GEMM
+// The gradient GEMMs of the stash path with the stash -> G' conversion inside the A-operand path, so that the B x B
+// strips make no separate trip through HBM (the in-place pass is 17 % of the north-star step and executes no flop).
+// The A operand never goes back to shared memory: TMA delivers the raw stash tile, eight converter warps (thread =
+// accumulator row = TMEM lane) multiply it by the rank-2 factor R1_i C1_j + R2_i C2_j, subtract the identity term in
+// fp32, round to fp16 and write it with tcgen05.st into one of four 32-column TMEM slots beside the 384-column
+// accumulator (384 + 4 * 32 = 512 columns); the MMAs take A from TMEM.  Shared-memory traffic per k block is that of
+// the plain kernel (the converter's read replaces the tensor core's read of A), which is what bounded the in-smem
+// conversion of round 1.  Values are bit-identical to backward_scale_kernel + gemm_wide_kernel: same fp32 expression,
+// same rounding, same MMA order.
+//   warps 0-7   epilogue (as gemm_wide_kernel)
+//   warps 8-15  converters: lane quarter q = warp & 3; warps 8-11 take the even k blocks, 12-15 the odd ones (a warp
+//               needs ~2 k-block times per block it converts: two barrier waits, the loads, ~280 instructions, the
+//               TMEM store and its completion; splitting one block over two warps left that latency on every block)
+//   warp 16     TMA producer of the raw stash tiles + k-side factors   (ring of kRawStages)
+//   warp 17     TMA producer of the B operand                          (ring of kBStages)
+//   warp 18     MMA issuer (leader CTA)
+// Two rings because the two operands have different latencies and lifetimes: the stash streams from HBM (2-3 k-block
+// times away) but is only needed until it is converted; the B operand comes from L2 and has to stay until its MMAs
+// have completed.  With one 5-stage ring the conversion sat in the middle of the load -> MMA -> free -> load cycle and
+// the kernel ran at (HBM latency + conversion + MMA) / 5 per k block.
+constexpr int kConvWarps = 8;
+constexpr int kASlots = 4;
+constexpr int kConvWn = 384;
+constexpr int kRawStages = 6;
+constexpr int kBStages = 4;
+constexpr int kConvFacBytes = 512;                             // 64 pair-interleaved fp32 k-side factor pairs per stage
+constexpr int kRawBytes = kRawStages * A_STAGE_BYTES;          // raw tiles (1 KiB aligned for the 128-byte swizzle),
+                                                               // then the factor blocks, then the B ring
+constexpr int kConvBBytes = kConvWn * 64;                      // 24 KiB of B per CTA and k block
+
+struct ConvBarriers {
+  uint64_t bfull[kBStages];     // leader: the B bytes of both CTAs have landed
+  uint64_t bempty[kBStages];    // each CTA: the MMAs that read this B slot have completed (1 commit)
+  uint64_t araw[kRawStages];    // each CTA: its raw A tile and the k-side factors have landed
+  uint64_t aempty[kRawStages];  // each CTA: the four converter warps of the block's parity are done with the raw tile
+  uint64_t aconv[kASlots];      // leader: the slot is converted in both CTAs (2 x 4 warp arrivals)
+  uint64_t afree[kASlots];      // each CTA: the MMAs that read the slot have completed (1 commit)
+  uint64_t tmem_full;
+  uint64_t tmem_empty;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(32 * (8 + kConvWarps + 3), 1) gemm_conv_kernel(const __grid_constant__ GemmParams P) {
+  constexpr int EW = 8, S = 2;
+  constexpr int kProducer = EW + kConvWarps, kProducerB = kProducer + 1, kIssuer = kProducer + 2;
+  constexpr int n2 = kConvWn - 256;
+  __shared__ ConvBarriers bars;
+  uint8_t* smem = aligned_dyn_smem();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t half = cluster_ctarank();
+  const int cluster_id = blockIdx.x / 2, num_clusters = gridDim.x / 2;
+  const int total = P.total_tiles;
+
+  if (warp == kProducer && lane == 0) {
+    for (int i = 0; i < kBStages; ++i) {
+      mbar_init(&bars.bfull[i], 1);
+      mbar_init(&bars.bempty[i], 1);
+    }
+    for (int i = 0; i < kRawStages; ++i) {
+      mbar_init(&bars.araw[i], 1);
+      mbar_init(&bars.aempty[i], kConvWarps / 2);
+    }
+    for (int i = 0; i < kASlots; ++i) {
+      mbar_init(&bars.aconv[i], kConvWarps);  // 4 warps (one per lane quarter) of each CTA
+      mbar_init(&bars.afree[i], 1);
+    }
+    mbar_init(&bars.tmem_full, 1);
+    mbar_init(&bars.tmem_empty, 2 * EW);
+    fence_mbar_init();
+  }
+  if (warp == kIssuer) {
+    tmem_alloc<2>(&bars.tmem_base, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars.tmem_base);
+  const uint32_t smem0 = smem_u32(smem);                     // raw ring: kRawStages tiles, then kRawStages factor blocks
+  uint8_t* smem_f = smem + kRawBytes;
+  uint8_t* smem_b = smem_f + kRawStages * kConvFacBytes;     // B ring: kBStages x 24 KiB (99 KiB in: 1 KiB aligned)
+  const uint32_t smem_b0 = smem_u32(smem_b);
+  const uint32_t a_slot0 = tmem_base + kConvWn;              // four 32-column A slots behind the accumulator
+
+  if (warp == kProducer) {  // raw stash tiles + k-side factors -> this CTA's araw barriers
+    const bool elected = elect_one();
+    RingState rs;
+    const uint32_t araw0 = smem_u32(&bars.araw[0]);
+    for (int u = cluster_id; u < total; u += num_clusters) {
+      const Tile tile = decode_wide(P, u);
+      const Job& job = P.jobs[tile.job];
+      const int m0 = tile.m0 + static_cast<int>(half) * BM;
+      for (int s = 0; s < job.nseg; ++s) {
+        const CUtensorMap* ma = P.maps + job.seg[s].map_a;
+        const int a_mn = job.seg[s].a_mn, p = job.seg[s].pair;
+        // k-side factors, pair-interleaved (b1_k, b1_k+1, b2_k, b2_k+1), 512 bytes per k block: row role (K-major A)
+        // k = global column -> the column factors; column role k = local row -> the row factors
+        const int kld = a_mn ? P.ld_row : P.ld_col;
+        const float* kpk = (a_mn ? P.fac_row : P.fac_col) + static_cast<size_t>(6 + 2 * p) * kld;
+        int kb_lo, kb_hi;
+        split_range(job.seg[s].num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          mbar_wait_bounded<false>(&bars.aempty[rs.stage], rs.phase ^ 1u, 1);
+          if (elected) {
+            const uint32_t sa = smem0 + rs.stage * A_STAGE_BYTES;
+            const uint32_t abar = araw0 + rs.stage * 8;
+            const int k = kb * BK;
+            mbar_expect_tx_u32(abar, A_STAGE_BYTES + kConvFacBytes);
+            if (!a_mn) {
+              tma_load_2d_u32(sa, ma, abar, k, m0);
+            } else {
+              tma_load_2d_u32(sa, ma, abar, m0, k);
+              tma_load_2d_u32(sa + MN_BOX_BYTES, ma, abar, m0 + 64, k);
+            }
+            bulk_load_1d_u32(smem0 + kRawBytes + rs.stage * kConvFacBytes, kpk + 2 * k, kConvFacBytes, abar);
+          }
+          rs.advance(kRawStages);
+        }
+      }
+    }
+  } else if (warp == kProducerB) {  // B operand of both CTAs -> the leader's bfull barriers
+    const bool elected = elect_one();
+    RingState rs;
+    const uint32_t bfull_loc0 = smem_u32(&bars.bfull[0]);
+    const uint32_t bfull_sig0 = mapa(bfull_loc0, 0);
+    for (int u = cluster_id; u < total; u += num_clusters) {
+      const Tile tile = decode_wide(P, u);
+      const Job& job = P.jobs[tile.job];
+      const int nb1 = tile.n0 + static_cast<int>(half) * 128;
+      const int nb2 = tile.n0 + 256 + static_cast<int>(half) * (n2 / 2);
+      for (int s = 0; s < job.nseg; ++s) {
+        const CUtensorMap* mb = P.maps + job.seg[s].map_b;
+        int kb_lo, kb_hi;
+        split_range(job.seg[s].num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+        for (int kb = kb_lo; kb < kb_hi; ++kb) {
+          mbar_wait_bounded<false>(&bars.bempty[rs.stage], rs.phase ^ 1u, 1);
+          if (elected) {
+            const uint32_t sb = smem_b0 + rs.stage * kConvBBytes;
+            const uint32_t bbar = bfull_sig0 + rs.stage * 8;
+            const int k = kb * BK;
+            if (half == 0) mbar_expect_tx_u32(bfull_loc0 + rs.stage * 8, 2 * kConvBBytes);
+            tma_load_2d_2sm_u32(sb, mb, bbar, nb1, k);
+            tma_load_2d_2sm_u32(sb + MN_BOX_BYTES, mb, bbar, nb1 + 64, k);
+            tma_load_2d_2sm_u32(sb + 2 * MN_BOX_BYTES, mb, bbar, nb2, k);
+          }
+          rs.advance(kBStages);
+        }
+      }
+    }
+  } else if (warp == kIssuer) {
+    if (half == 0) {
+      const bool elected = elect_one();
+      RingState rs, as;
+      int it = 0;
+      const uint32_t bempty0 = smem_u32(&bars.bempty[0]);
+      const uint32_t afree0 = smem_u32(&bars.afree[0]);
+      const uint32_t tfull = smem_u32(&bars.tmem_full);
+      constexpr uint32_t hi = smem_desc_hi_sw128(1024);
+      // A comes from TMEM (always "K-major"), B is MN-major in shared memory
+      constexpr uint32_t idesc1 = make_idesc_f16(2 * BM, 256, 0, 0, 1);
+      constexpr uint32_t idesc2 = make_idesc_f16(2 * BM, n2, 0, 0, 1);
+      for (int u = cluster_id; u < total; u += num_clusters, ++it) {
+        const Tile tile = decode_wide(P, u);
+        const Job& job = P.jobs[tile.job];
+        mbar_wait_bounded<false>(&bars.tmem_empty, (it & 1) ^ 1u, 4);
+        tc_fence_after();
+        uint32_t accumulate = 0;
+        for (int s = 0; s < job.nseg; ++s) {
+          int kb_lo, kb_hi;
+          split_range(job.seg[s].num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+          for (int kb = kb_lo; kb < kb_hi; ++kb) {
+            mbar_wait_bounded<false>(&bars.bfull[rs.stage], rs.phase, 2);
+            mbar_wait_bounded<true>(&bars.aconv[as.stage], as.phase, 5);  // arrivals come from both CTAs
+            tc_fence_after();
+            if (elected) {
+              const uint32_t b_lo = smem_desc_lo(smem_b0 + rs.stage * kConvBBytes, MN_BOX_BYTES);
+              const uint32_t a_t = a_slot0 + as.stage * 32;
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                umma_f16_ts_2sm(tmem_base, a_t + k * 8, smem_desc_join(b_lo + k * OperandDesc<true>::kStep, hi), idesc1,
+                                accumulate);
+                umma_f16_ts_2sm(tmem_base + 256, a_t + k * 8,
+                                smem_desc_join(b_lo + ((2 * MN_BOX_BYTES) >> 4) + k * OperandDesc<true>::kStep, hi), idesc2,
+                                accumulate);
+                accumulate = 1;
+              }
+              umma_commit_2sm_u32(bempty0 + rs.stage * 8, 0b11);  // the B slot (both CTAs)
+              umma_commit_2sm_u32(afree0 + as.stage * 8, 0b11);   // the TMEM slot
+            }
+            rs.advance(kBStages);
+            as.advance(kASlots);
+          }
+        }
+        if (elected) umma_commit_2sm_u32(tfull, 0b11);
+      }
+    }
+  } else if (warp >= EW) {
+    // ---- converters.  A warp converts 32 accumulator rows (its TMEM lane quarter) x 64 k of every other k block.
+    //   row role (K-major raw tile): thread = row; 4 x LDS.128 of its swizzled 128-byte row, 16 packed factor entries,
+    //     one tcgen05.st.32x32b.x16.
+    //   column role (MN-major raw tile, the accumulator row is a COLUMN of the stash): ldmatrix.trans with row addresses
+    //     chosen so that every thread receives, for its lanes (t/4, t/4 + 8), the k pairs 4 (t%4) + 2 c + {0, 1} + 16 n --
+    //     exactly the register layout of tcgen05.st.16x256b; 4 m-side factor pairs in registers, 4 k-side entries.
+    const int cw = warp - EW;
+    const int q = cw & 3, parity = cw >> 2;
+    RingState rs, as;
+    int kcount = 0;  // k blocks seen so far (all tiles): this warp converts those with kcount % 2 == parity
+    const uint32_t aconv_sig0 = mapa(smem_u32(&bars.aconv[0]), 0);
+    const uint32_t aempty0 = smem_u32(&bars.aempty[0]);
+    float mxsg = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) mxsg = fmaxf(mxsg, fabsf(expf(P.t3[r]) * P.g3[r]));
+    auto slot_ready = [&]() {
+      mbar_wait_bounded<false>(&bars.araw[rs.stage], rs.phase, 6);
+      mbar_wait_bounded<true>(&bars.afree[as.stage], as.phase ^ 1u, 7);
+      tc_fence_after();
+    };
+    auto slot_done = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_u32(aempty0 + rs.stage * 8);  // every lane has read its part of the raw tile
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_u32(aconv_sig0 + as.stage * 8);  // counted in the leader CTA
+      rs.advance(kRawStages);
+      as.advance(kASlots);
+    };
+    // G' pair = E~ pair * (a1 b1 + a2 b2) in fp32, rounded to fp16; `entry` = (b1_k, b1_k+1, b2_k, b2_k+1)
+    auto convert_pair = [&](uint32_t e2, unsigned long long a1p, unsigned long long a2p, const ulonglong2& entry, float& lo,
+                            float& hi) {
+      const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&e2));
+      unpack2(fmul2(pack2(e.x, e.y), ffma2(a1p, entry.x, fmul2(a2p, entry.y))), lo, hi);
+    };
+    for (int u = cluster_id; u < total; u += num_clusters) {
+      const Tile tile = decode_wide(P, u);
+      const Job& job = P.jobs[tile.job];
+      const int tile_row0 = tile.m0 + static_cast<int>(half) * BM + q * 32;  // first output row of this warp
+      for (int s = 0; s < job.nseg; ++s) {
+        const int a_mn = job.seg[s].a_mn, p = job.seg[s].pair;
+        const float kcp = mxsg > 0.f ? kKappa * expf(P.t3[p]) * P.g3[p] / mxsg : 0.f;
+        int kb_lo, kb_hi;
+        split_range(job.seg[s].num_kb, tile.split, job.ksplits, kb_lo, kb_hi);
+        if (!a_mn) {
+          // ---------------- row role: thread = row `mrow`, k = global column
+          const int row = q * 32 + lane;
+          const int mrow = tile_row0 + lane;
+          const float* mf = P.fac_row + static_cast<size_t>(p) * 2 * P.ld_row;
+          const float a1 = mrow < P.ld_row ? __ldg(mf + mrow) : 0.f;
+          const float a2 = mrow < P.ld_row ? __ldg(mf + P.ld_row + mrow) : 0.f;
+          const unsigned long long a1p = pack2(a1, a1), a2p = pack2(a2, a2);
+          const int kdiag = P.row_offset + mrow;  // the positive pair of this row sits at this global column
+          const uint32_t row_off = static_cast<uint32_t>(row) * 128u;
+          const uint32_t sw = static_cast<uint32_t>(row & 7);
+          for (int kb = kb_lo; kb < kb_hi; ++kb, ++kcount) {
+            if ((kcount & 1) != parity) {
+              rs.advance(kRawStages);
+              as.advance(kASlots);
+              continue;
+            }
+            slot_ready();
+            const uint8_t* sa_g = smem + rs.stage * A_STAGE_BYTES + row_off;
+#pragma unroll 1
+            for (int kh = 0; kh < 2; ++kh) {  // the two 32-k halves of the block
+            const uint8_t* sf_g = smem_f + rs.stage * kConvFacBytes + kh * 256;
+            uint32_t out[16];
+            const int dk = kdiag - (kb * BK + kh * 32);  // in [0, 32): element dk of this thread is the positive pair
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              // 8 k: 16-byte chunk (4 kh + c) of the row, at position chunk ^ (row & 7).  Plain loads (not volatile asm):
+              // the compiler may batch them; the barrier waits above carry memory clobbers, nothing moves across them
+              const uint4 raw = *reinterpret_cast<const uint4*>(sa_g + (((static_cast<uint32_t>(kh * 4 + c)) ^ sw) << 4));
+              const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const ulonglong2 entry = *reinterpret_cast<const ulonglong2*>(sf_g + (c * 4 + t) * 16);
+                float lo, hi;
+                convert_pair(w4[t], a1p, a2p, entry, lo, hi);
+                out[c * 4 + t] = pack_half2(lo, hi);
+              }
+            }
+            if (static_cast<unsigned>(dk) < 32u) {  // rare: redo the pair that holds the identity term, in fp32
+              const int j = dk >> 1;
+              const uint32_t e2 = *reinterpret_cast<const uint32_t*>(
+                  sa_g + (((static_cast<uint32_t>(kh * 4 + (j >> 2))) ^ sw) << 4) + (j & 3) * 4);
+              const ulonglong2 entry = *reinterpret_cast<const ulonglong2*>(sf_g + j * 16);
+              float lo, hi;
+              convert_pair(e2, a1p, a2p, entry, lo, hi);
+              if (dk & 1) hi -= kcp;
+              else lo -= kcp;
+              const uint32_t fixed = pack_half2(lo, hi);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i == j) out[i] = fixed;
+            }
+            tmem_st_32x32b_x16(a_slot0 + as.stage * 32 + kh * 16 + (static_cast<uint32_t>(q * 32) << 16), out);
+            }
+            slot_done();
+          }
+        } else {
+          // ---------------- column role: accumulator row = global column of the stash, k = local row
+          const int t4 = lane >> 2, tq = lane & 3;
+          const float* mf = P.fac_col + static_cast<size_t>(p) * 2 * P.ld_col;
+          unsigned long long a1p[2][2], a2p[2][2];  // [g][h]: lanes 16 g + 8 h + t / 4 of this warp's quarter
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int mrow = tile_row0 + 16 * g + 8 * h + t4;
+              const float a1 = mrow < P.ld_col ? __ldg(mf + mrow) : 0.f;
+              const float a2 = mrow < P.ld_col ? __ldg(mf + P.ld_col + mrow) : 0.f;
+              a1p[g][h] = pack2(a1, a1);
+              a2p[g][h] = pack2(a2, a2);
+            }
+          // ldmatrix row addresses: lane L supplies row r = L & 7 of matrix j = L >> 3 = 2 h + c:
+          //   k row (within the block)  32 kh + 16 n + 4 (r >> 1) + 2 c + (r & 1),  m chunk of (32 q + 16 g + 8 h)
+          const int lj = lane >> 3, lr = lane & 7;
+          const int lh = lj >> 1, lc = lj & 1;
+          const int kk0 = 4 * (lr >> 1) + 2 * lc + (lr & 1);  // + 16 n + 32 kh
+          uint32_t ld_off[2][2];  // [g][n]: byte offset inside a stage, for kh = 0 (kh = 1: + 32 rows = 4096 bytes; the
+                                  // swizzle term only depends on kk & 7, which 32 more rows do not change)
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              const int m_local = q * 32 + 16 * g + 8 * lh;  // first of the 8 m of this matrix (CTA-local accumulator row)
+              const int kk = kk0 + 16 * n;
+              ld_off[g][n] = static_cast<uint32_t>((m_local >> 6) * MN_BOX_BYTES + kk * 128 +
+                                                   ((((m_local & 63) >> 3) ^ (kk & 7)) << 4));
+            }
+          for (int kb = kb_lo; kb < kb_hi; ++kb, ++kcount) {
+            if ((kcount & 1) != parity) {
+              rs.advance(kRawStages);
+              as.advance(kASlots);
+              continue;
+            }
+            slot_ready();
+#pragma unroll 1
+            for (int kh = 0; kh < 2; ++kh) {  // the two 32-k halves of the block
+            const uint32_t sa = smem0 + rs.stage * A_STAGE_BYTES + kh * 4096;
+            const uint8_t* sf_g = smem_f + rs.stage * kConvFacBytes + kh * 256;
+            ulonglong2 entry[2][2];  // [n][c]: k pair 32 kh + 16 n + 4 (t % 4) + 2 c of the block
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+              for (int c = 0; c < 2; ++c)
+                entry[n][c] = *reinterpret_cast<const ulonglong2*>(sf_g + (8 * n + 2 * tq + c) * 16);
+            const int krow0 = P.row_offset + kb * BK + kh * 32;  // global row of this warp's first k
+            // identity term: element (lane 16 g + 8 h + t / 4, k 16 n + 4 (t % 4) + 2 c + {0, 1}) is a positive pair when
+            // d0 + 16 g + 8 h - 16 n - 2 c is 0 or 1; only threads with d0 in [-24, 19] can hold one (rare: one warp
+            // per 32 columns and k block), the others take the loop without the per-element test
+            const int d0 = (tile_row0 + t4) - (krow0 + 4 * tq);
+            auto convert_half = [&](int g, auto diag_tag) {
+              constexpr bool kDiag = decltype(diag_tag)::value;
+              uint32_t out[8];
+#pragma unroll
+              for (int n = 0; n < 2; ++n) {
+                uint32_t r4[4];
+                ldmatrix_x4_trans(sa + ld_off[g][n], r4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int h = j >> 1, c = j & 1;
+                  float lo, hi;
+                  convert_pair(r4[j], a1p[g][h], a2p[g][h], entry[n][c], lo, hi);
+                  if constexpr (kDiag) {  // in fp32, before the rounding to fp16
+                    const int dj = d0 + 16 * g + 8 * h - 16 * n - 2 * c;
+                    if (dj == 0) lo -= kcp;
+                    if (dj == 1) hi -= kcp;
+                  }
+                  out[4 * n + j] = pack_half2(lo, hi);
+                }
+              }
+              tmem_st_16x256b_x2(a_slot0 + as.stage * 32 + kh * 16 + (static_cast<uint32_t>(q * 32 + 16 * g) << 16), out);
+            };
+            if (__any_sync(0xffffffffu, d0 >= -24 && d0 <= 19)) {
+              convert_half(0, std::true_type{});
+              convert_half(1, std::true_type{});
+            } else {
+              convert_half(0, std::false_type{});
+              convert_half(1, std::false_type{});
+            }
+            }
+            slot_done();
+          }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue (as gemm_wide_kernel)
+    const int q = warp & 3;
+    const int slice = warp >> 2;
+    constexpr int cs = kConvWn / S;
+    float alpha = P.alpha0;
+    {
+      float mx = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(P.t3[r]) * P.g3[r]));
+      alpha *= mx;
+    }
+    int it = 0;
+    for (int u = cluster_id; u < total; u += num_clusters, ++it) {
+      const Tile tile = decode_wide(P, u);
+      const int j = tile.job;
+      const bool accumulate_out = P.jobs[j].ksplits > 1;
+      const int orow = tile.m0 + static_cast<int>(half) * BM + q * 32 + lane;
+      const bool row_ok = orow < P.m[j];
+      const int ncols = P.n[j];
+      const int c0 = tile.n0 + slice * cs;
+      float* outp = P.out[j] + static_cast<size_t>(orow) * P.ldc[j] + c0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slice * cs;
+      mbar_wait_bounded<false>(&bars.tmem_full, it & 1, 3);
+      tc_fence_after();
+      constexpr int nch = cs / 32;
+      for (int ch = 0; ch < nch; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (ch == nch - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (half == 0) mbar_arrive(&bars.tmem_empty);
+            else mbar_arrive_cluster(&bars.tmem_empty, 0);
+          }
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const int col = c0 + ch * 32 + k4 * 4;
+            if (col + 3 < ncols) {
+              float4 o;
+              o.x = __uint_as_float(v[k4 * 4 + 0]) * alpha;
+              o.y = __uint_as_float(v[k4 * 4 + 1]) * alpha;
+              o.z = __uint_as_float(v[k4 * 4 + 2]) * alpha;
+              o.w = __uint_as_float(v[k4 * 4 + 3]) * alpha;
+              float* dst = outp + ch * 32 + k4 * 4;
+              if (!accumulate_out) *reinterpret_cast<float4*>(dst) = o;
+              else red_add_v4(dst, o);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync();
+  if (warp == kIssuer) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host launchers
 }  // namespace
 
@@ -1675,6 +2130,18 @@ int launch_gemm(const GemmParams& p, int cg, int ew, int max_sms, cudaStream_t s
 int wide_stages(int wn) {
   const int st = (227 * 1024 - 2048) / (A_STAGE_BYTES + wn * 64);
   return st > kMaxStages ? kMaxStages : st;
+}
+
+int conv_stages() { return kBStages; }
+
+int launch_gemm_conv(const GemmParams& p, int max_sms, cudaStream_t stream) {
+  if (p.total_tiles <= 0) return SCLIP_OK;
+  if (p.wn != kConvWn) {
+    set_error("internal: the converting GEMM takes 384-column tiles (got %d)", p.wn);
+    return SCLIP_ERR_ARGUMENT;
+  }
+  const int smem = kRawStages * (A_STAGE_BYTES + kConvFacBytes) + kBStages * kConvBBytes + 1024;
+  return launch_persistent(gemm_conv_kernel, p, 2, 8 + kConvWarps + 1, smem, p.total_tiles, max_sms, stream);
 }
 
 int launch_gemm_wide(const GemmParams& p, int ew, int max_sms, cudaStream_t stream) {

@@ -404,9 +404,17 @@ class _CudaBackend:
         _lib.check(self.lib.sclip_backward_scale(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
                    "sclip_backward_scale")
 
-    def backward_gemms_role(self, ws, t3, g3, role, max_sms=0):
-        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role), int(max_sms),
-                                                      _stream()), "sclip_backward_gemms_role")
+    def backward_gemms_role(self, ws, t3, g3, role, max_sms=0, convert=False):
+        _lib.check(self.lib.sclip_backward_gemms_role(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), int(role),
+                                                      1 if convert else 0, int(max_sms), _stream()),
+                   "sclip_backward_gemms_role")
+
+    def gemm_converts_stash(self, ws):
+        return bool(self.lib.sclip_gemm_converts_stash(byref(ws.pb)))
+
+    def backward_factors(self, ws, t3, g3):
+        _lib.check(self.lib.sclip_backward_factors(byref(ws.pb), ws.ptr, _ptr(t3), _ptr(g3), _stream()),
+                   "sclip_backward_factors")
 
     def push_shards(self, ws, max_blocks, block_threads=1024, epoch=0):
         _lib.check(self.lib.sclip_push_shards(byref(ws.pb), ws.ptr, ws.peer_ptrs, int(max_blocks), int(block_threads),
@@ -605,17 +613,26 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
     dimg, dtxt, daud = (torch.empty(img.shape, dtype=gdtype, device=img.device) for _ in range(3))
     dt3 = torch.empty(3, dtype=torch.float32, device=img.device)
     stashed = bool(getattr(ws, "stashed", False))
+    # stash path: an in-place HBM pass converts the stash to G' before the gradient GEMMs (default).
+    # SCLIP_CONVERT_IN_GEMM=1 selects the experimental GEMM that converts in its A-operand path through tensor memory
+    # (dim 768 only).  It is bit-identical but SLOWER on B200 at 32768 x 768: 12.7-13.3 ms against 2.6 + 8.0 ms for
+    # pass + GEMM, over five variants -- opt-in for A/B measurements, not the product path.
+    convert = (stashed and not be.allows_cpu and os.environ.get("SCLIP_CONVERT_IN_GEMM", "0") == "1"
+               and be.gemm_converts_stash(ws))
     _mark("backward_begin")
     if stashed:
-        ws.stashed = False  # converted in place: this stash can serve one backward only
-        be.backward_scale(ws, t3, g3)
+        ws.stashed = False  # a stash serves one backward (the in-place pass consumes it)
+        if convert:
+            be.backward_factors(ws, t3, g3)
+        else:
+            be.backward_scale(ws, t3, g3)
     else:
         be.backward_tiles(ws, t3, g3)
     _mark("backward_tiles")
     col = None
     mult = 1.0
     if pb.world == 1:
-        be.backward_gemms_role(ws, t3, g3, 0)
+        be.backward_gemms_role(ws, t3, g3, 0, convert=convert)
         _mark("backward_gemms")
     else:
         import torch.distributed as dist
@@ -632,7 +649,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             # (NVLink loads, side stream) while the row-role GEMMs run on the remaining SMs
             cur = torch.cuda.current_stream()
             comm = _comm_stream(img.device)
-            be.backward_gemms_role(ws, t3, g3, 1)
+            be.backward_gemms_role(ws, t3, g3, 1, convert=convert)
             _mark("backward_gemms_col")
             done = torch.cuda.Event()
             done.record(cur)
@@ -652,19 +669,20 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
             if trace:
                 global _LAST_COMM_EVENTS
                 _LAST_COMM_EVENTS = (_LAST_COMM_EVENTS or []) + [("bwd_barrier", bar_done), ("pull_reduce", reduced)]
-            be.backward_gemms_role(ws, t3, g3, 2, max_sms=(_sm_count(img.device) - cfg.comm_sms) if cfg.overlap else 0)
+            be.backward_gemms_role(ws, t3, g3, 2, max_sms=(_sm_count(img.device) - cfg.comm_sms) if cfg.overlap else 0,
+                                   convert=convert)
             _mark("backward_gemms_row")
             cur.wait_event(reduced)
             _mark("backward_gemms")
         elif not (cfg.overlap and img.is_cuda):
-            be.backward_gemms_role(ws, t3, g3, 0)
+            be.backward_gemms_role(ws, t3, g3, 0, convert=convert)
             _mark("backward_gemms")
             scatter()
             _mark("reduce_scatter")
         else:
             cur = torch.cuda.current_stream()
             comm = _comm_stream(img.device)
-            be.backward_gemms_role(ws, t3, g3, 1)  # column role first ...
+            be.backward_gemms_role(ws, t3, g3, 1, convert=convert)  # column role first ...
             done = torch.cuda.Event()
             done.record(cur)
             with torch.cuda.stream(comm):
@@ -672,7 +690,7 @@ def _backward_impl(ws: _Workspace, img, txt, aud, t3, g3, cfg: TriContrastiveCon
                 scatter()                            # ... its reduce-scatter runs under the row-role GEMMs
                 reduced = torch.cuda.Event()
                 reduced.record(comm)
-            be.backward_gemms_role(ws, t3, g3, 2, max_sms=_sm_count(img.device) - cfg.comm_sms)
+            be.backward_gemms_role(ws, t3, g3, 2, max_sms=_sm_count(img.device) - cfg.comm_sms, convert=convert)
             cur.wait_event(reduced)
             _mark("backward_gemms")
         if cfg.grad_scale == "ddp":

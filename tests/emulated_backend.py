@@ -191,7 +191,7 @@ class EmulatedBackend:
     def backward_gemms(self, ws, t3, g3):
         self.backward_gemms_role(ws, t3, g3, 0)
 
-    def backward_gemms_role(self, ws, t3, g3, role, max_sms=0):
+    def backward_gemms_role(self, ws, t3, g3, role, max_sms=0, convert=False):
         bl, bg, d, off = self._dims(ws)
         lay = ws.lay
         mx, _ = self._coeffs(t3, g3)

@@ -45,7 +45,7 @@ class _Rank:
         return self.blob[int(offset):int(offset) + n].view(dtype).view(*shape)
 
 
-def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch, grad_mult, steps=2):
+def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch, grad_mult, steps=2, convert=True):
     from synergy_clip_b200 import _lib
 
     lib = _lib.load()
@@ -81,15 +81,19 @@ def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch,
         for r, rk in enumerate(ranks):  # (a real run: barrier first)
             _lib.check(lib.sclip_forward_loss_peers(byref(rk.pb), rk.ptr, table, _p(loss[r]), st), "forward_loss_peers")
         for rk in ranks:
-            if stash:
+            conv = 1 if (stash and convert and lib.sclip_gemm_converts_stash(byref(rk.pb))) else 0
+            if stash and conv:
+                _lib.check(lib.sclip_backward_factors(byref(rk.pb), rk.ptr, _p(t3), _p(g3), st), "backward_factors")
+            elif stash:
                 _lib.check(lib.sclip_backward_scale(byref(rk.pb), rk.ptr, _p(t3), _p(g3), st), "backward_scale")
             else:
                 _lib.check(lib.sclip_backward_tiles(byref(rk.pb), rk.ptr, _p(t3), _p(g3), st), "backward_tiles")
-            _lib.check(lib.sclip_backward_gemms_role(byref(rk.pb), rk.ptr, _p(t3), _p(g3), 1, 0, st), "gemms column role")
+            _lib.check(lib.sclip_backward_gemms_role(byref(rk.pb), rk.ptr, _p(t3), _p(g3), 1, conv, 0, st), "gemms column role")
         grads = []
         for r, rk in enumerate(ranks):  # (a real run: barrier first, pull-reduce on the side stream under the row role)
             _lib.check(lib.sclip_pull_reduce_cols(byref(rk.pb), rk.ptr, table, 16, 512, st), "pull_reduce_cols")
-            _lib.check(lib.sclip_backward_gemms_role(byref(rk.pb), rk.ptr, _p(t3), _p(g3), 2, 128, st), "gemms row role")
+            conv = 1 if (stash and convert and lib.sclip_gemm_converts_stash(byref(rk.pb))) else 0
+            _lib.check(lib.sclip_backward_gemms_role(byref(rk.pb), rk.ptr, _p(t3), _p(g3), 2, conv, 128, st), "gemms row role")
             d3 = [torch.empty((rows_local, dim), dtype=torch.float32, device="cuda") for _ in range(3)]
             dt = torch.empty(3, device="cuda")
             col = rk.view(rk.lay.col_contrib, (3, rows_local, dim), torch.float32)
@@ -107,6 +111,7 @@ def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch,
 
 @pytest.mark.parametrize("world,rows_local,dim,dtype_name,math_name,stash,single_launch,tol", [
     (2, 512, 768, "bfloat16", "f16", True, True, 1e-3),     # the bench configuration in small: stash + one-launch forward
+                                                            # + conversion inside the role-split GEMMs
     (4, 256, 768, "bfloat16", "f16", True, True, 1e-3),
     (4, 256, 512, "bfloat16", "f16", False, True, 1e-3),    # recompute backward behind the one-launch forward
     (2, 320, 256, "float32", "f16x3", False, False, 1e-5),  # ragged shards (no 256 multiple): plain column order, fp32 parity
@@ -125,3 +130,15 @@ def test_emulated_ranks_match_global_batch_oracle(world, rows_local, dim, dtype_
         assert golden_util.rel(got, want[key]) < tol, key
     dscale = np.mean([g[1].double().cpu().numpy() for g in grads], axis=0)  # DDP's mean over ranks
     assert np.max(np.abs(dscale - want["dscale"])) / np.max(np.abs(want["dscale"])) < tol
+
+
+def test_conversion_in_the_gemm_is_bit_identical_to_the_hbm_pass():
+    """dim 768: the GEMM kernel that converts the stash in its A-operand path (tensor memory) must give exactly what the
+    in-place HBM pass + the plain GEMM kernel give -- same fp32 expression, same rounding to fp16, same MMA order --
+    for the row role and the column role separately (the sharded path launches them one by one)."""
+    a = _run_sharded(2, 512, 768, torch.bfloat16, "f16", True, True, 2.0, steps=1, convert=True)[1]
+    b = _run_sharded(2, 512, 768, torch.bfloat16, "f16", True, True, 2.0, steps=1, convert=False)[1]
+    for (ga, dta), (gb, dtb) in zip(a[1], b[1]):
+        for x, y in zip(ga, gb):
+            assert torch.equal(x, y)
+        assert torch.equal(dta, dtb)

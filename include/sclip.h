@@ -207,6 +207,8 @@ int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3
  * through tensor memory, never back to HBM or shared memory) from the factor arrays of sclip_backward_factors.  The
  * values are those of sclip_backward_scale + the plain GEMMs, bit for bit.  Only where sclip_gemm_converts_stash()
  * says so (fp16 operands and gradient tiles of 384 columns, e.g. dim 768).  The stash survives the call.
+ * EXPERIMENTAL: measured slower than sclip_backward_scale + the plain GEMMs on B200 (12.7-13.3 ms against 10.6 ms at
+ * 32768 x 768); the repo's host op does not use it unless SCLIP_CONVERT_IN_GEMM=1.
  * max_sms > 0: at most that many SMs (see sclip_forward_tiles_cols). */
 #define SCLIP_GEMM_CONVERT_STASH 1
 int sclip_backward_gemms_role(const sclip_problem* problem, void* ws, const float* t3, const float* g3, int role,

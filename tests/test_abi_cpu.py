@@ -52,6 +52,20 @@ def test_plan_rejects_bad_problems(bad):
     assert len(_lib.load().sclip_last_error()) > 0
 
 
+def test_converting_gemm_predicate_is_host_arithmetic():
+    """sclip_gemm_converts_stash: 1 only for fp16 operands and 384-column gradient tiles (dim 768); a convert flag on any
+    other problem is an argument error, not a launch."""
+    lib = _lib.load()
+    yes = _lib.Problem(512, 512, 0, 768, _lib.SCLIP_BF16, _lib.MATH_F16, 1, 0)
+    assert lib.sclip_gemm_converts_stash(ctypes.byref(yes)) == 1
+    for pb in (_lib.Problem(512, 512, 0, 512, _lib.SCLIP_BF16, _lib.MATH_F16, 1, 0),
+               _lib.Problem(512, 512, 0, 768, _lib.SCLIP_F32, _lib.MATH_F16X3, 1, 0)):
+        assert lib.sclip_gemm_converts_stash(ctypes.byref(pb)) == 0
+        assert lib.sclip_backward_gemms_role(ctypes.byref(pb), None, None, None, 0, 1, 0, None) == -1
+    assert lib.sclip_gemm_converts_stash(None) == 0
+    assert lib.sclip_backward_factors(ctypes.byref(yes), None, None, None, None) == -1
+
+
 def test_null_arguments_are_errors_not_crashes():
     lib = _lib.load()
     assert lib.sclip_plan(None, None) == -1

@@ -253,7 +253,9 @@ int sclip_cosine_logits(const void* a, const void* b, const float* log_scale, in
  * DESTINATION's `sync` area (system-scope release), which that rank's forward tiles launched with
  * SCLIP_FWD_WAIT_PEERS acquire.  No barrier is needed before the call: the exchange buffers exist twice
  * (problem->parity, alternate it every step), and a peer that is still one step behind reads the other copy.
- * At most max_blocks thread blocks of block_threads (<= 1024) threads, on the SMs the tile kernel leaves free (max_sms). */
+ * At most max_blocks thread blocks of block_threads (<= 1024) threads, on the SMs the tile kernel leaves free (max_sms).
+ * max_blocks == 0: the bytes move on the copy engines instead (strided peer copies enqueued on `stream`, a one-thread
+ * kernel behind the copies to each destination publishes its flag): no SMs, the tile kernel may keep all of them. */
 int sclip_push_shards(const sclip_problem* problem, void* ws, void* const* peer_ws, int max_blocks, int block_threads,
                       int epoch, void* stream);
 

@@ -812,6 +812,14 @@ __global__ void __launch_bounds__(1024) push_shards_kernel(const PushShardArgs a
   }
 }
 
+// Copy-engine variant of the push (sclip_push_shards with max_blocks == 0): the bulk bytes go through strided
+// cudaMemcpy2DAsync calls (no SMs, so the similarity tiles keep all of them), and behind the copies to one destination
+// this one-thread kernel publishes landed[this rank] = epoch there.  Stream order puts it behind the completed copies.
+__global__ void publish_landed_kernel(int* flag, int epoch) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+
 // One small block that returns once every other rank's shard of this epoch has landed (for launches that do not wait
 // themselves: ragged shards, the collective-free fallback order).
 __global__ void wait_shards_kernel(const int* landed, int world, int rank, int epoch) {
@@ -1063,6 +1071,31 @@ int launch_push_shards(const Workspace& w, void* const* peer_ws, int max_blocks,
   a.rank = rank;
   a.arrived = reinterpret_cast<unsigned int*>(w.sync) + kSyncArrived;
   a.epoch = epoch;
+  if (max_blocks == 0) {  // copy engines
+    const size_t row0 = static_cast<size_t>(rank) * a.rows_local;
+    const size_t seg_bytes = static_cast<size_t>(a.rows_local) * a.dim * 2;
+    const size_t seg_pitch = static_cast<size_t>(a.rows_global) * a.dim * 2;
+    const size_t first = row0 * a.dim * 2;
+    for (int pi = 0; pi < a.count; ++pi) {
+      uint8_t* dst = a.peer[pi];
+      cudaError_t e = cudaMemcpy2DAsync(dst + a.xhat_off + first, seg_pitch, a.local + a.xhat_off + first, seg_pitch,
+                                        seg_bytes, 3, cudaMemcpyDeviceToDevice, stream);
+      if (e == cudaSuccess && a.nseg == 6)
+        e = cudaMemcpy2DAsync(dst + a.xhat_lo_off + first, seg_pitch, a.local + a.xhat_lo_off + first, seg_pitch,
+                              seg_bytes, 3, cudaMemcpyDeviceToDevice, stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(dst + a.diag_off + row0 * 4, static_cast<size_t>(a.rows_global) * 4,
+                              a.local + a.diag_off + row0 * 4, static_cast<size_t>(a.rows_global) * 4,
+                              static_cast<size_t>(a.rows_local) * 4, 3, cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) {
+        set_error("sclip_push_shards: peer copy to rank %d failed: %s", a.peer_rank[pi], cudaGetErrorString(e));
+        return SCLIP_ERR_CUDA;
+      }
+      publish_landed_kernel<<<1, 1, 0, stream>>>(reinterpret_cast<int*>(dst + a.sync_off) + kSyncLanded + rank, epoch);
+      SCLIP_LAUNCHED();
+    }
+    return SCLIP_OK;
+  }
   const int bx = max_blocks < 1 ? 1 : max_blocks;
   push_shards_kernel<<<bx, block_threads, 0, stream>>>(a);
   SCLIP_LAUNCHED();

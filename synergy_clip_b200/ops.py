@@ -45,7 +45,7 @@ class TriContrastiveConfig:
 
     def __init__(self, process_group=None, math: str = "auto", grad_scale: str = "ddp", grads_fp32: bool = False,
                  overlap: bool = True, comm_sms: int = 20, stash="auto", transport: str = "auto",
-                 check_status: bool = False):
+                 check_status: bool = False, push: str = "auto"):
         if math not in ("auto", "f16", "f16x3"):
             raise ValueError(f"math={math!r}")
         if grad_scale not in ("ddp", "sum"):
@@ -65,13 +65,22 @@ class TriContrastiveConfig:
         # world_size > 1: how the shards move between ranks.
         #   "p2p"  -- the workspace lives in symmetric memory (torch.distributed._symmetric_memory: every rank's blob
         #             mapped into every process over NVLink / NVSwitch) and the exchanges are kernels of the library
-        #             that load straight from the peers' workspaces (pull all-gather of the operand shards in waves
-        #             of 1, 2, 4 ranks under the tiles, pull reduce of the column-role gradients under the row-role GEMMs);
+        #             that store to / load from the peers' workspaces (push all-gather of the operand shards under
+        #             one flag-gated tile launch, pull reduce of the column-role gradients under the row-role GEMMs);
         #   "nccl" -- torch.distributed collectives (all-gather / reduce-scatter) on a side stream;
         #   "auto" -- "p2p" on CUDA when symmetric memory is available, else "nccl".
         if transport not in ("auto", "p2p", "nccl"):
             raise ValueError(f"transport={transport!r}")
         self.transport = transport
+        # transport "p2p": what moves the operand shards into the peers' workspaces.
+        #   "sm" -- a kernel of the library on `comm_sms` SMs (the similarity tiles get the rest);
+        #   "ce" -- the copy engines (strided peer copies + one-thread flag kernels): the tiles keep every SM;
+        #   "auto" -- the SCLIP_PUSH environment variable, else "sm".
+        if push not in ("auto", "sm", "ce"):
+            raise ValueError(f"push={push!r}")
+        self.push = push if push != "auto" else os.environ.get("SCLIP_PUSH", "sm")
+        if self.push not in ("sm", "ce"):
+            raise ValueError(f"SCLIP_PUSH={self.push!r}")
         # Read the device status word after every forward (one host synchronisation per call) and raise if a row or
         # column log-sum-exp was not finite.  Off by default: the losses are non-finite too in that case, which the
         # caller's own `.item()` (main_pretraining.py:169-170) shows without an extra sync.
@@ -575,8 +584,9 @@ def _forward_p2p(ws: "_SymmWorkspace", img, txt, aud, t3, cfg: TriContrastiveCon
     be.prologue(ws, img, txt, aud, t3, diag=stash)
     _mark("prologue")
     # the in-kernel wait needs the push kernels of all ranks to make progress next to the tile kernels: own SMs
-    pipelined = cfg.overlap and bl % 256 == 0 and cfg.comm_sms > 0
-    blocks = 2 * max(cfg.comm_sms, 4)  # 1024-thread blocks, two per SM left free by the tile kernel
+    ce = cfg.push == "ce"  # copy engines move the shards: no SMs set aside
+    pipelined = cfg.overlap and bl % 256 == 0 and (ce or cfg.comm_sms > 0)
+    blocks = 0 if ce else 2 * max(cfg.comm_sms, 4)  # 1024-thread blocks, two per SM left free by the tile kernel
     ready = torch.cuda.Event()
     ready.record(cur)
     trace = _TRACE is not None
@@ -589,7 +599,8 @@ def _forward_p2p(ws: "_SymmWorkspace", img, txt, aud, t3, cfg: TriContrastiveCon
         global _LAST_COMM_EVENTS
         _LAST_COMM_EVENTS = [("pushes", pushed)]
     if pipelined:
-        be.forward_tiles_cols(ws, t3, 7, 0, 0, stash, max_sms=_sm_count(dev) - cfg.comm_sms, wait_epoch=ws.epoch)
+        be.forward_tiles_cols(ws, t3, 7, 0, 0, stash, max_sms=0 if ce else _sm_count(dev) - cfg.comm_sms,
+                              wait_epoch=ws.epoch)
     else:
         # ragged shards, or no SMs set aside for the pushes: wait for every shard first, then the plain column order
         be.wait_shards(ws, ws.epoch)

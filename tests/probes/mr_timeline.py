@@ -72,6 +72,10 @@ for v in variants:
         run("p2p no-overlap", overlap=False)
     elif v == "nccl":
         run("nccl", transport="nccl")
+    elif v == "ce":
+        run("p2p copy-engine push", push="ce")
+    elif v == "sm":
+        run("p2p kernel push", push="sm")
     elif v.startswith("comm_sms="):
         run("p2p " + v, comm_sms=int(v.split("=")[1]))
 dist.destroy_process_group()

@@ -45,7 +45,8 @@ class _Rank:
         return self.blob[int(offset):int(offset) + n].view(dtype).view(*shape)
 
 
-def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch, grad_mult, steps=2, convert=True):
+def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch, grad_mult, steps=2, convert=True,
+                 push_blocks=8):
     from synergy_clip_b200 import _lib
 
     lib = _lib.load()
@@ -70,7 +71,7 @@ def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch,
             _lib.check(lib.sclip_prologue(byref(rk.pb), rk.ptr, *[_p(x) for x in shards[r]], _p(t3), 1 if stash else 0, st),
                        "prologue")
         for rk in ranks:  # (a real run: on the side stream, concurrently with the tiles)
-            _lib.check(lib.sclip_push_shards(byref(rk.pb), rk.ptr, table, 8, 1024, step, st), "push_shards")
+            _lib.check(lib.sclip_push_shards(byref(rk.pb), rk.ptr, table, push_blocks, 1024, step, st), "push_shards")
         for rk in ranks:
             if not single_launch:
                 _lib.check(lib.sclip_wait_shards(byref(rk.pb), rk.ptr, step, st), "wait_shards")
@@ -130,6 +131,24 @@ def test_emulated_ranks_match_global_batch_oracle(world, rows_local, dim, dtype_
         assert golden_util.rel(got, want[key]) < tol, key
     dscale = np.mean([g[1].double().cpu().numpy() for g in grads], axis=0)  # DDP's mean over ranks
     assert np.max(np.abs(dscale - want["dscale"])) / np.max(np.abs(want["dscale"])) < tol
+
+
+@pytest.mark.parametrize("world,rows_local,dim,dtype_name,math_name,stash", [
+    (4, 256, 768, "bfloat16", "f16", True),
+    (2, 256, 512, "float32", "f16x3", False),   # six operand segments (hi + lo)
+])
+def test_copy_engine_push_is_bit_identical_to_the_kernel_push(world, rows_local, dim, dtype_name, math_name, stash):
+    """sclip_push_shards with max_blocks == 0 moves the shards with strided peer copies and publishes the flags from a
+    one-thread kernel: same bytes in the same places, so everything downstream must be identical."""
+    dtype = getattr(torch, dtype_name)
+    a = _run_sharded(world, rows_local, dim, dtype, math_name, stash, True, 1.0, steps=2, push_blocks=8)[1]
+    b = _run_sharded(world, rows_local, dim, dtype, math_name, stash, True, 1.0, steps=2, push_blocks=0)[1]
+    for la, lb in zip(a[0], b[0]):
+        assert torch.equal(la, lb)
+    for (da, ta), (db, tb) in zip(a[1], b[1]):
+        assert torch.equal(ta, tb)
+        for x, y in zip(da, db):
+            assert torch.equal(x, y)
 
 
 def test_conversion_in_the_gemm_is_bit_identical_to_the_hbm_pass():

@@ -75,10 +75,11 @@ class TriContrastiveConfig:
         # transport "p2p": what moves the operand shards into the peers' workspaces.
         #   "sm" -- a kernel of the library on `comm_sms` SMs (the similarity tiles get the rest);
         #   "ce" -- the copy engines (strided peer copies + one-thread flag kernels): the tiles keep every SM;
-        #   "auto" -- the SCLIP_PUSH environment variable, else "sm".
+        #   "auto" -- the SCLIP_PUSH environment variable, else "ce" (8 GPUs, 32768 x 768, bench.py, three alternating
+        #             pairs on two boxes: 2.25 / 2.32 / 2.35 ms against 2.39 / 2.46 / 2.42 ms with "sm").
         if push not in ("auto", "sm", "ce"):
             raise ValueError(f"push={push!r}")
-        self.push = push if push != "auto" else os.environ.get("SCLIP_PUSH", "sm")
+        self.push = push if push != "auto" else os.environ.get("SCLIP_PUSH", "ce")
         if self.push not in ("sm", "ce"):
             raise ValueError(f"SCLIP_PUSH={self.push!r}")
         # Read the device status word after every forward (one host synchronisation per call) and raise if a row or

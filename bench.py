@@ -467,7 +467,7 @@ def main():
     # dominant kernel: the gradient GEMM launch (6 of the 9 contractions = 12 B^2 D / world flops per launch)
     gemm_ms = st.get("backward_gemms")
     gemm_tf = 12.0 * b * b * d / world / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None
-    stashed = dt_name == "bf16" and d >= 640
+    stashed = dt_name == "bf16" and d >= 512
     stage_rates = {}
     if st.get("forward_tiles"):
         stage_rates["forward_tiles_tflops"] = 6.0 * b * b * d / world / (st["forward_tiles"] * 1e-3) / 1e12

@@ -189,7 +189,11 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
 /* The same tiles without recomputation, after a forward with SCLIP_FWD_STASH: in place on grad_tiles,
  *   G'_ij = E~_ij (R1_i C1_j + R2_i C2_j) - kappa c_p [i == j]   (= kappa c_p ((softmax_rows + softmax_cols)/2 - I));
  * the identity term is subtracted in fp32 before the rounding to fp16, so the positive-pair entry keeps its
- * precision when the softmax is sharply peaked.  HBM-bound elementwise pass. */
+ * precision when the softmax is sharply peaked.  HBM-bound elementwise pass.  When the stash cannot carry the
+ * gradient (status word 1, see sclip_read_status: a saturated element, a vanishing loss, a scale >= 44) a recompute
+ * launch behind the pass (the kernel of sclip_backward_tiles; it returns at once otherwise) writes G' instead -- decided
+ * on the device, no host synchronisation, same results as sclip_backward_tiles.  (The converting GEMMs of
+ * SCLIP_GEMM_CONVERT_STASH have no such fallback.) */
 int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream);
 
 /* dxhat_row[m] = G'_{rowpair(m)} . xhat_{col modality}   (rows_local x dim, complete)
@@ -270,11 +274,21 @@ int sclip_pull_reduce_cols(const sclip_problem* problem, void* ws, const void* c
 
 /* Copy the four device status words of the workspace to the host (synchronises `stream`).  status_host[0] != 0: a row
  * or column log-sum-exp of the last forward was not finite (non-finite embeddings, or exp(logit_scale) beyond what
- * fp32 can hold); the losses are then non-finite too. */
+ * fp32 can hold); the losses are then non-finite too.  status_host[1] != 0 (complete after sclip_backward_scale): the
+ * fp16 stash of this step was not used, because it could not carry the gradient to 1e-3 --
+ *   bit 0: an element sits at fp16's saturation value (a negative pair whose logit exceeds the mean of its two
+ *          positive-pair logits by more than ln(16 * 65504) = 13.86), found by the conversion pass;
+ *   bit 1: one of the losses is below 0.03: the softmax is so peaked that what is left of the gradient sits in elements
+ *          the stash holds with few or no bits (its window ends 6.9 nats below the positive pairs).  world == 1 and the
+ *          peer-memory loss only: a rank that sees only its share of the loss does not apply this test;
+ *   bit 2: a scale exp(t_p) >= 44: a handful of elements carry each row and the fp16 rounding of G' no longer averages
+ *          out of dlogit_scale, which the stash route derives from the rounded G' (1.4e-3 .. 2.1e-3 measured at 100).
+ * Nothing is wrong in any of these cases: sclip_backward_scale reads the same word on the device and a recompute launch
+ * behind the pass (the kernel of sclip_backward_tiles) writes G' instead, at that kernel's cost for the step. */
 int sclip_read_status(const sclip_problem* problem, void* ws, int32_t* status_host, void* stream);
 
 /* ---- single-GPU convenience (world == 1): the whole tail in two calls ---------------------------
- * keep_for_backward != 0: sclip_backward will follow on the same workspace.  With SCLIP_MATH_F16 and dim >= 640 the
+ * keep_for_backward != 0: sclip_backward will follow on the same workspace.  With SCLIP_MATH_F16 and dim >= 512 the
  * forward then stashes its tiles and the backward converts them (4 bytes of HBM traffic per logit instead of 2 dim
  * flop: the measured crossover); otherwise the backward recomputes the similarities.  0: forward only (evaluation
  * loops).  A stash serves ONE backward: a second sclip_backward on the same forward returns SCLIP_ERR_ARGUMENT. */

@@ -121,6 +121,23 @@ constexpr int kSyncFinishDone = 32;  // block counter of sclip_backward_finish
 constexpr int kSyncLossDone = 33;    // [3] block counters of the loss kernel
 constexpr int kSyncWords = 64;
 
+// status words of a workspace (sclip_read_status)
+constexpr int kStatusNonFinite = 0;      // a row / column log-sum-exp of the last forward was not finite
+constexpr int kStatusStashOverflow = 1;  // non-zero: the backward recomputes G' instead of converting the stash.
+                                         //   bit 0 (set by the conversion pass): a stash element sits at fp16's
+                                         //          saturation value (a negative pair more than 13.86 nats above the
+                                         //          mean of its two positive pairs);
+                                         //   bit 1 (forward_loss_kernel): a loss is below kStashMinLoss -- the softmax
+                                         //          is so peaked that what is left of the gradient sits in elements the
+                                         //          stash keeps with few or no bits (its fp16 window ends 6.9 nats below
+                                         //          the positive pairs);
+                                         //   bit 2 (backward_factors_kernel): a scale exp(t_p) >= kStashMaxScale.  There a
+                                         //          handful of elements carry each row and their fp16 rounding no longer
+                                         //          averages out of dlogit_scale, which the stash route derives from the
+                                         //          rounded G' (measured 1.4e-3 .. 2.1e-3 at s = 100; 3.9e-4 at 43.5)
+constexpr float kStashMinLoss = 0.03f;
+constexpr float kStashMaxScale = 44.0f;  // = the limit of the folded-exponent forward (kFoldMaxScale)
+
 struct FwdParams {
   CUtensorMap maps[kFwdMaps];
   Job jobs[3];
@@ -164,6 +181,7 @@ struct BwdParams {
   int nti, ntj;
   int stages;
   float acc_scale;
+  const int* only_if;  // when non-null the kernel does nothing unless *only_if != 0 (stash overflow fallback)
 };
 
 struct GemmParams {

@@ -459,6 +459,9 @@ int sclip_forward_diag(const sclip_problem* problem, void* ws, const float* t3, 
   return launch_diag(w, t3, static_cast<cudaStream_t>(stream));
 }
 
+static int backward_tiles_impl(const Workspace& w, const float* t3, const float* g3, const int* only_if,
+                               cudaStream_t stream);
+
 int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
   Workspace w;
   int rc = resolve(problem, ws, &w);
@@ -467,7 +470,11 @@ int sclip_backward_scale(const sclip_problem* problem, void* ws, const float* t3
     set_error("sclip_backward_scale needs t3, g3 and a SCLIP_MATH_F16 problem");
     return SCLIP_ERR_ARGUMENT;
   }
-  return launch_backward_scale(w, t3, g3, static_cast<cudaStream_t>(stream));
+  rc = launch_backward_scale(w, t3, g3, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  // a stash element outside fp16's range (status word kStatusStashOverflow, set by the forward): the pass above has
+  // skipped itself and this launch recomputes G' from the similarities; otherwise it returns before touching anything
+  return backward_tiles_impl(w, t3, g3, w.status + kStatusStashOverflow, static_cast<cudaStream_t>(stream));
 }
 
 int sclip_forward_tiles_cols(const sclip_problem* problem, void* ws, const float* t3, int pair_mask,
@@ -563,6 +570,11 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
     set_error("t3 / g3 is null");
     return SCLIP_ERR_ARGUMENT;
   }
+  return backward_tiles_impl(w, t3, g3, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+static int backward_tiles_impl(const Workspace& w, const float* t3, const float* g3, const int* only_if,
+                               cudaStream_t stream) {
   BwdParams p;
   memset(&p, 0, sizeof(p));
   MapTable tab(w, p.maps, kBwdMaps);
@@ -587,7 +599,8 @@ int sclip_backward_tiles(const sclip_problem* problem, void* ws, const float* t3
   p.ntj = w.lay.col_tiles;
   p.stages = ring_stages(staging_slabs(epi_warps(), x3));
   p.acc_scale = x3 ? 1.0f / (kOperandScaleX3 * kOperandScaleX3) : 1.0f;
-  return launch_backward_tiles(p, cta_group(), epi_warps(), static_cast<cudaStream_t>(stream));
+  p.only_if = only_if;
+  return launch_backward_tiles(p, cta_group(), epi_warps(), stream);
 }
 
 int sclip_backward_gemms(const sclip_problem* problem, void* ws, const float* t3, const float* g3, void* stream) {
@@ -974,7 +987,7 @@ int sclip_forward(const sclip_problem* problem, void* ws, const void* img, const
   }
   // stash when a backward follows, the operands are fp16 and the row is long enough that 4 bytes of HBM traffic per
   // logit beat 2 dim flop of recomputation (measured crossover on B200 between dim 512 and 768)
-  const bool stash = keep_for_backward && problem != nullptr && problem->math == SCLIP_MATH_F16 && problem->dim >= 640;
+  const bool stash = keep_for_backward && problem != nullptr && problem->math == SCLIP_MATH_F16 && problem->dim >= 512;
   int rc = sclip_prologue(problem, ws, img, txt, aud, t3, stash ? SCLIP_PRO_DIAG : 0, stream);
   if (!rc) rc = sclip_forward_tiles_cols(problem, ws, t3, 7, 0, 1 << 30, stash ? SCLIP_FWD_STASH : 0, 0, 0, stream);
   if (!rc) rc = sclip_forward_reduce(problem, ws, stream);

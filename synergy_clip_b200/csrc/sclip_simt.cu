@@ -337,6 +337,7 @@ struct LossArgs {
   float* loss_part;
   float* loss3;
   int rows_local, rows_global, row_offset, world, row_blocks;
+  int* status;  // non-null when `loss` below is a complete loss (world == 1 or peer mode): the peaked-softmax guard
 };
 
 __device__ __forceinline__ float ld_relaxed_sys(const float* p) {  // peer data: L2 only, never a stale L1 line
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(kLossCols) forward_loss_kernel(const LossArgs 
       const float loss = static_cast<float>(v / (2.0 * a.rows_global));
       a.loss_part[p] = loss;
       if (a.loss3 != nullptr) a.loss3[p] = loss;
+      if (a.status != nullptr && loss < kStashMinLoss) atomicOr(a.status + kStatusStashOverflow, 2);
     }
   }
 }
@@ -591,6 +593,7 @@ struct FactorArgs {
   float* fac_col;         // [3][2][ld_col]
   int rows_local, rows_global, row_offset;
   int ld_row, ld_col;
+  int* fallback;          // status word kStatusStashOverflow (bit 2: a scale beyond kStashMaxScale)
 };
 
 __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs a) {
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(256) backward_factors_kernel(const FactorArgs 
 #pragma unroll
   for (int r = 0; r < 3; ++r) mx = fmaxf(mx, fabsf(expf(a.t3[r]) * a.g3[r]));
   const float cp = mx > 0.f ? expf(a.t3[p]) * a.g3[p] / mx : 0.f;
+  if (i == 0 && a.fallback != nullptr && expf(a.t3[p]) >= kStashMaxScale) atomicOr(a.fallback, 4);
   const float k8 = 8.0f * kKappa * cp;  // (kappa c_p / 2) * 16: the stash carries a 2^-4 headroom factor
   if (i < a.ld_row) {
     float r1 = 0.f, r2 = 0.f;
@@ -646,6 +650,8 @@ struct ScaleArgs {
   int rows_local, rows_global, ld;
   int ld_row, ld_col;
   int row_offset;
+  int* fallback;  // status word kStatusStashOverflow: non-zero on entry -> the pass does nothing (the recompute kernel
+                  // launched behind it produces G'); the pass itself sets bit 0 when it meets a saturated element
 };
 
 // packed fp32 pairs (FFMA2 / FMUL2): half the floating-point instructions of the scalar form -- at the clock the power
@@ -672,7 +678,7 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long x, unsigne
 template <bool DIAG>
 __device__ __forceinline__ void scale_rows(__half* ptr, size_t ld, const float* fr1, const float* fr2, int nrows,
                                            const unsigned long long (&c1)[4], const unsigned long long (&c2)[4], int d0,
-                                           float kcp) {
+                                           float kcp, uint32_t& seen_max) {
   constexpr int kBatch = 4;  // rows loaded before the first is stored (the pass is in place: the compiler must not be
                              // left to order a row's load behind the previous row's store)
   for (int r0 = 0; r0 < nrows; r0 += kBatch) {
@@ -694,6 +700,10 @@ __device__ __forceinline__ void scale_rows(__half* ptr, size_t ld, const float* 
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        {  // largest raw stash value seen by this thread (the stash is non-negative; 0x7BFF = saturated in the forward)
+          const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&seen_max), *reinterpret_cast<const __half2*>(&w[k]));
+          seen_max = *reinterpret_cast<const uint32_t*>(&m);
+        }
         const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
         const unsigned long long v = mul2(pk2(e.x, e.y), fma2(r1p, c1[k], mul2(r2p, c2[k])));
         float lo, hi;
@@ -711,6 +721,7 @@ __device__ __forceinline__ void scale_rows(__half* ptr, size_t ld, const float* 
 }
 
 __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) {
+  if (a.fallback != nullptr && (*reinterpret_cast<const volatile int*>(a.fallback) & ~1) != 0) return;
   const int p = blockIdx.z;
   const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (col >= a.rows_global) return;
@@ -735,10 +746,12 @@ __global__ void __launch_bounds__(256) backward_scale_kernel(const ScaleArgs a) 
   __half* ptr = a.g + (static_cast<size_t>(p) * a.rows_local + row0) * a.ld + col;
   const int d0 = a.row_offset + row0 - col;  // row r holds the positive pair at column offset d0 + r of this thread
   const int g0 = a.row_offset + row0, bc0 = blockIdx.x * 2048;  // block-uniform: does the diagonal cross this block?
+  uint32_t seen_max = 0;
   if (g0 + kScaleRows > bc0 && g0 < bc0 + 2048)
-    scale_rows<true>(ptr, a.ld, fr + row0, fr + a.ld_row + row0, nrows, c1, c2, d0, kcp);
+    scale_rows<true>(ptr, a.ld, fr + row0, fr + a.ld_row + row0, nrows, c1, c2, d0, kcp, seen_max);
   else
-    scale_rows<false>(ptr, a.ld, fr + row0, fr + a.ld_row + row0, nrows, c1, c2, d0, kcp);
+    scale_rows<false>(ptr, a.ld, fr + row0, fr + a.ld_row + row0, nrows, c1, c2, d0, kcp, seen_max);
+  if (a.fallback != nullptr && ((seen_max & 0xFFFFu) >= 0x7BFFu || (seen_max >> 16) >= 0x7BFFu)) atomicOr(a.fallback, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ peer memory
@@ -966,6 +979,7 @@ int launch_forward_loss(const Workspace& w, const float* col_lse_all, const void
   a.row_offset = w.pb.row_offset;
   a.world = w.pb.world;
   a.row_blocks = reduce_row_blocks(w.pb);
+  a.status = (w.pb.world == 1 || peer_ws != nullptr) ? w.status : nullptr;
   forward_loss_kernel<<<dim3(loss_col_chunks(w.pb), 3), kLossCols, 0, stream>>>(a);
   SCLIP_LAUNCHED();
   return SCLIP_OK;
@@ -1025,7 +1039,7 @@ int launch_diag(const Workspace& w, const float* t3, cudaStream_t stream) {
 int launch_backward_factors(const Workspace& w, const float* t3, const float* g3, cudaStream_t stream) {
   const int ld_row = (w.pb.rows_local + 63) / 64 * 64, ld_col = (w.pb.rows_global + 63) / 64 * 64;
   FactorArgs f{t3, g3, w.diag_all, w.lse_row, w.lse_col, w.fac_row, w.fac_col,
-               w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, ld_row, ld_col};
+               w.pb.rows_local, w.pb.rows_global, w.pb.row_offset, ld_row, ld_col, w.status + kStatusStashOverflow};
   const int n = ld_row > ld_col ? ld_row : ld_col;
   backward_factors_kernel<<<dim3((n + 255) / 256, 3), 256, 0, stream>>>(f);
   SCLIP_LAUNCHED();
@@ -1037,7 +1051,7 @@ int launch_backward_scale(const Workspace& w, const float* t3, const float* g3, 
   if (rc) return rc;
   const int ld_row = (w.pb.rows_local + 63) / 64 * 64, ld_col = (w.pb.rows_global + 63) / 64 * 64;
   ScaleArgs a{w.g[0], w.fac_row, w.fac_col, t3, g3, w.pb.rows_local, w.pb.rows_global, w.lay.ld_g, ld_row, ld_col,
-              w.pb.row_offset};
+              w.pb.row_offset, w.status + kStatusStashOverflow};  // (ScaleArgs::fallback)
   dim3 grid((w.pb.rows_global + 2047) / 2048, (w.pb.rows_local + kScaleRows - 1) / kScaleRows, 3);
   backward_scale_kernel<<<grid, 256, 0, stream>>>(a);
   SCLIP_LAUNCHED();

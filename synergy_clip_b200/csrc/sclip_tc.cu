@@ -364,7 +364,8 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// saturating variant: values above 65504 (a stash element more than ~14 nats above both positive pairs) clamp
+// saturating variant: values above 65504 (a stash element more than ~14 nats above both positive pairs) clamp to 65504;
+// backward_scale_kernel recognises that value and hands the step over to the recompute kernel
 __device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -1043,6 +1044,8 @@ __global__ void __launch_bounds__(64 + 32 * EW, 1) backward_tiles_kernel(const _
   const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
   const int nti_c = P.nti / CG;
   const int total = 3 * nti_c * P.ntj;
+  // fallback launch behind backward_scale_kernel: only when the forward reported a stash overflow (same word for every CTA)
+  if (P.only_if != nullptr && *reinterpret_cast<const volatile int*>(P.only_if) == 0) return;
 
   const uint32_t tmem_base = kernel_setup<CG, EW>(&bars, warp, lane);
 

@@ -58,7 +58,8 @@ class TriContrastiveConfig:
         self.comm_sms = comm_sms
         # fp16-operand mode only: store the scaled exponentials of every tile in the forward ("stash") and convert them
         # in place in the backward (4 bytes of HBM traffic per logit) instead of recomputing the similarity matrices
-        # (2 D flop per logit).  "auto": stash when D >= 640 -- measured crossover on B200 (D = 512: recompute wins).
+        # (2 D flop per logit).  "auto": stash when D >= 512 -- measured on B200 (D = 512: 0.740 against 0.754 ms at 8192 rows,
+        # 11.3-11.5 against 12.2 ms at 32768; below that the recompute is the cheaper side and stays the choice).
         if stash not in ("auto", True, False):
             raise ValueError(f"stash={stash!r}")
         self.stash = stash
@@ -489,7 +490,7 @@ def _forward_stages(ws: _Workspace, img, txt, aud, t3, cfg: TriContrastiveConfig
     exponentials of every tile (the "stash") so that the backward does not recompute the similarity matrices."""
     be = _BACKEND
     pb, lay = ws.pb, ws.lay
-    stash = bool(keep) and pb.math == MATH_F16 and (pb.dim >= 640 if cfg.stash == "auto" else bool(cfg.stash))
+    stash = bool(keep) and pb.math == MATH_F16 and (pb.dim >= 512 if cfg.stash == "auto" else bool(cfg.stash))
     ws.stashed = stash
     _mark("begin")
     loss3 = torch.empty(3, dtype=torch.float32, device=img.device)

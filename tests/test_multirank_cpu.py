@@ -209,3 +209,20 @@ def test_wave_major_tile_order_matches_the_pull_order(world, row_tiles):
         assert waves == sorted(waves)
         for wave, _, _, tj in order:
             assert tj // tiles_per_rank == (rank - wave) % world
+
+
+def test_config_validates_its_knobs(monkeypatch):
+    """TriContrastiveConfig: unknown values raise; `push="auto"` follows SCLIP_PUSH and defaults to the copy engines."""
+    from synergy_clip_b200 import ops
+
+    for kw in (dict(math="fp8"), dict(grad_scale="mean"), dict(stash="yes"), dict(transport="mpi"), dict(push="dma")):
+        with pytest.raises(ValueError):
+            ops.TriContrastiveConfig(**kw)
+    monkeypatch.delenv("SCLIP_PUSH", raising=False)
+    assert ops.TriContrastiveConfig().push == "ce"
+    monkeypatch.setenv("SCLIP_PUSH", "sm")
+    assert ops.TriContrastiveConfig().push == "sm"
+    assert ops.TriContrastiveConfig(push="ce").push == "ce"
+    monkeypatch.setenv("SCLIP_PUSH", "nvlink")
+    with pytest.raises(ValueError):
+        ops.TriContrastiveConfig()

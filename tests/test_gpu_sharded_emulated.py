@@ -46,7 +46,7 @@ class _Rank:
 
 
 def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch, grad_mult, steps=2, convert=True,
-                 push_blocks=8):
+                 push_blocks=8, t3_values=T3, status_out=None):
     from synergy_clip_b200 import _lib
 
     lib = _lib.load()
@@ -59,7 +59,7 @@ def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch,
     table = (ctypes.c_void_p * world)(*[r.blob.data_ptr() for r in ranks])
     shards = [[torch.from_numpy(e[r * rows_local:(r + 1) * rows_local].copy()).cuda().to(dtype) for e in embs]
               for r in range(world)]
-    t3 = torch.tensor(T3, dtype=torch.float32, device="cuda")
+    t3 = torch.tensor(t3_values, dtype=torch.float32, device="cuda")
     g3 = torch.tensor(W3, dtype=torch.float32, device="cuda")
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     col_tiles = ranks[0].lay.col_tiles
@@ -106,6 +106,10 @@ def _run_sharded(world, rows_local, dim, dtype, math_name, stash, single_launch,
         status = (ctypes.c_int32 * 4)()
         _lib.check(lib.sclip_read_status(byref(ranks[0].pb), ranks[0].ptr, status, st), "read_status")
         assert status[0] == 0
+        if status_out is not None:
+            for rk in ranks:
+                _lib.check(lib.sclip_read_status(byref(rk.pb), rk.ptr, status, st), "read_status")
+                status_out.append(status[1])
         out = (loss, grads)
     return embs, out
 
@@ -149,6 +153,24 @@ def test_copy_engine_push_is_bit_identical_to_the_kernel_push(world, rows_local,
         assert torch.equal(ta, tb)
         for x, y in zip(da, db):
             assert torch.equal(x, y)
+
+
+def test_sharded_stash_falls_back_to_recompute_at_a_large_scale():
+    """Every rank stashes in the forward, finds exp(t) >= 44 in its backward (status word 1, bit 2) and recomputes its
+    strip of G' instead of converting the stash: the sharded result must still be the global-batch oracle's."""
+    t3 = (float(np.log(100.0)), 2.9, float(np.log(60.0)))
+    flags = []
+    embs, (loss, grads) = _run_sharded(2, 256, 768, torch.bfloat16, "f16", True, True, 2.0, steps=2, convert=False,
+                                       t3_values=t3, status_out=flags)
+    assert flags and all(f & 4 for f in flags), flags
+    want = closed_form.tri_contrastive(*embs, t3, W3)
+    for l in loss:
+        assert np.max(np.abs(l.double().cpu().numpy() - want["loss"]) / want["loss"]) < 1e-3
+    for m, key in enumerate(("dimg", "dtxt", "daud")):
+        got = np.concatenate([g[0][m].double().cpu().numpy() for g in grads], axis=0) / 2.0
+        assert golden_util.rel(got, want[key]) < 1e-3, key
+    dscale = np.mean([g[1].double().cpu().numpy() for g in grads], axis=0)
+    assert np.max(np.abs(dscale - want["dscale"])) / np.max(np.abs(want["dscale"])) < 1e-3
 
 
 def test_conversion_in_the_gemm_is_bit_identical_to_the_hbm_pass():
